@@ -1,0 +1,196 @@
+"""Python face of the native library with the reference extension's five entry points.
+
+The reference registers `rasterize_gaussians`, `rasterize_gaussians_backward`, `voxelize_gaussians`,
+`voxelize_gaussians_backward`, `mark_visible` in its pybind module `_C` (SUB/ext.cpp:17-23; argument
+lists SUB/rasterize_points.h:18-61, SUB/voxelize_points.cu:29-167).  This module offers the same five
+callables with the same positional arguments and return tuples, implemented over the C ABI of
+libr2xray.so (include/r2x.h) with raw device pointers.  torch is used for device memory and the current
+stream only.  There is no CPU path: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import ALLOC_FN, check, load
+
+__all__ = [
+    "rasterize_gaussians",
+    "rasterize_gaussians_backward",
+    "voxelize_gaussians",
+    "voxelize_gaussians_backward",
+    "mark_visible",
+]
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    """float32, contiguous, on `dev` (empty tensors stay empty)."""
+    if t.numel() == 0:
+        return t
+    if t.device != dev:
+        if t.device.type != "cuda":
+            t = t.to(dev)  # small host-side settings tensors (e.g. campos) only
+        else:
+            raise ValueError(f"tensor on {t.device}, expected {dev}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t) -> int | None:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RuntimeError(
+            f"{name} must be a CUDA tensor: the B200 rasterizer/voxelizer has no CPU fallback "
+            f"(got {getattr(t, 'device', type(t))})"
+        )
+
+
+class _BinningAlloc:
+    """Allocator handed to the synchronous forward for the R-dependent binning buffer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, nbytes, _user):
+        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.tensor.data_ptr()
+
+
+def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                        projmatrix, tan_fovx, tan_fovy, image_height, image_width, campos, prefiltered, mode,
+                        debug):
+    """-> (num_rendered, out_color[1,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)."""
+    _require_cuda(means3D, "means3D")
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    lib = load()
+    dev = means3D.device
+    P, H, W = int(means3D.shape[0]), int(image_height), int(image_width)
+    with torch.cuda.device(dev):
+        means3D = _f32(means3D, dev); opacity = _f32(opacity, dev)
+        scales = _f32(scales, dev); rotations = _f32(rotations, dev); cov3D_precomp = _f32(cov3D_precomp, dev)
+        viewmatrix = _f32(viewmatrix, dev); projmatrix = _f32(projmatrix, dev); campos = _f32(campos, dev)
+        out_color = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty(lib.r2x_raster_geom_bytes(P), dtype=torch.uint8, device=dev)
+        img = torch.empty(lib.r2x_raster_image_bytes(W, H), dtype=torch.uint8, device=dev)
+        alloc = _BinningAlloc(dev)
+        nr = C.c_int(0)
+        rc = lib.r2x_raster_forward(
+            torch.cuda.current_stream(dev).cuda_stream, P, W, H, _ptr(means3D), _ptr(opacity), _ptr(scales),
+            float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix),
+            _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), int(mode),
+            out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(), alloc.cb, None, int(bool(debug)),
+            C.byref(nr))
+        check(rc, "r2x_raster_forward")
+    return nr.value, out_color, radii, geom, alloc.tensor, img
+
+
+def rasterize_gaussians_backward(means3D, radii, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                                 projmatrix, tan_fovx, tan_fovy, dL_dout_color, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, mode, debug):
+    """-> (dL_dmeans2D[P,3], dL_dopacity[P,1], dL_dmu[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
+    dL_dscales[P,3], dL_drotations[P,4])."""
+    _require_cuda(means3D, "means3D")
+    lib = load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    H, W = int(dL_dout_color.shape[-2]), int(dL_dout_color.shape[-1])
+    with torch.cuda.device(dev):
+        means3D = _f32(means3D, dev); scales = _f32(scales, dev); rotations = _f32(rotations, dev)
+        cov3D_precomp = _f32(cov3D_precomp, dev); viewmatrix = _f32(viewmatrix, dev)
+        projmatrix = _f32(projmatrix, dev); campos = _f32(campos, dev); dL = _f32(dL_dout_color, dev)
+        opts = dict(dtype=torch.float32, device=dev)
+        g_mean2D = torch.empty((P, 3), **opts); g_op = torch.empty((P, 1), **opts); g_mu = torch.empty((P, 1), **opts)
+        g_mean3D = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
+        g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        scratch = torch.empty(lib.r2x_raster_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
+        rc = lib.r2x_raster_backward(
+            torch.cuda.current_stream(dev).cuda_stream, P, int(R), W, H, _ptr(means3D), _ptr(scales),
+            float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix),
+            _ptr(campos), float(tan_fovx), float(tan_fovy), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
+            _ptr(imageBuffer), scratch.data_ptr(), _ptr(dL), _ptr(g_mean2D), _ptr(g_op), _ptr(g_mu),
+            _ptr(g_mean3D), _ptr(g_cov), _ptr(g_scale), _ptr(g_rot), int(mode), int(bool(debug)))
+        check(rc, "r2x_raster_backward")
+    return g_mean2D, g_op, g_mu, g_mean3D, g_cov, g_scale, g_rot
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """-> bool[P]: view-space z > 0.2 (RAS/auxiliary.h:143-168)."""
+    _require_cuda(means3D, "means3D")
+    lib = load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    with torch.cuda.device(dev):
+        means3D = _f32(means3D, dev); viewmatrix = _f32(viewmatrix, dev); projmatrix = _f32(projmatrix, dev)
+        present = torch.zeros((P,), dtype=torch.bool, device=dev)
+        rc = lib.r2x_mark_visible(torch.cuda.current_stream(dev).cuda_stream, P, _ptr(means3D), _ptr(viewmatrix),
+                                  _ptr(projmatrix), _ptr(present))
+        check(rc, "r2x_mark_visible")
+    return present
+
+
+def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3D_precomp, nVoxel_x, nVoxel_y,
+                       nVoxel_z, sVoxel_x, sVoxel_y, sVoxel_z, center_x, center_y, center_z, prefiltered, debug):
+    """-> (num_rendered, out_volume[nx,ny,nz], radii_x, radii_y, radii_z, geomBuffer, binningBuffer, imgBuffer)."""
+    _require_cuda(means3D, "means3D")
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    lib = load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    nx, ny, nz = int(nVoxel_x), int(nVoxel_y), int(nVoxel_z)
+    with torch.cuda.device(dev):
+        means3D = _f32(means3D, dev); opacity = _f32(opacity, dev)
+        scales = _f32(scales, dev); rotations = _f32(rotations, dev); cov3D_precomp = _f32(cov3D_precomp, dev)
+        vol = torch.empty((nx, ny, nz), dtype=torch.float32, device=dev)
+        rx = torch.empty((P,), dtype=torch.int32, device=dev)
+        ry = torch.empty_like(rx); rz = torch.empty_like(rx)
+        geom = torch.empty(lib.r2x_voxel_geom_bytes(P), dtype=torch.uint8, device=dev)
+        img = torch.empty(lib.r2x_voxel_image_bytes(nx, ny, nz), dtype=torch.uint8, device=dev)
+        alloc = _BinningAlloc(dev)
+        nr = C.c_int(0)
+        rc = lib.r2x_voxel_forward(
+            torch.cuda.current_stream(dev).cuda_stream, P, nx, ny, nz, float(sVoxel_x), float(sVoxel_y),
+            float(sVoxel_z), float(center_x), float(center_y), float(center_z), _ptr(means3D), _ptr(opacity),
+            _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), int(bool(prefiltered)),
+            vol.data_ptr(), _ptr(rx), _ptr(ry), _ptr(rz), geom.data_ptr(), img.data_ptr(), alloc.cb, None,
+            int(bool(debug)), C.byref(nr))
+        check(rc, "r2x_voxel_forward")
+    return nr.value, vol, rx, ry, rz, geom, alloc.tensor, img
+
+
+def voxelize_gaussians_backward(means3D, radii_x, radii_y, radii_z, scales, rotations, scale_modifier,
+                                cov3D_precomp, dL_dout, geomBuffer, R, binningBuffer, imageBuffer, nVoxel_x,
+                                nVoxel_y, nVoxel_z, sVoxel_x, sVoxel_y, sVoxel_z, center_x, center_y, center_z,
+                                debug):
+    """-> (dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dscales[P,3], dL_drotations[P,4])."""
+    _require_cuda(means3D, "means3D")
+    lib = load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    with torch.cuda.device(dev):
+        means3D = _f32(means3D, dev); scales = _f32(scales, dev); rotations = _f32(rotations, dev)
+        cov3D_precomp = _f32(cov3D_precomp, dev); dL = _f32(dL_dout, dev)
+        opts = dict(dtype=torch.float32, device=dev)
+        g_op = torch.empty((P, 1), **opts); g_mean = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
+        g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        scratch = torch.empty(lib.r2x_voxel_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
+        rc = lib.r2x_voxel_backward(
+            torch.cuda.current_stream(dev).cuda_stream, P, int(R), int(nVoxel_x), int(nVoxel_y), int(nVoxel_z),
+            float(sVoxel_x), float(sVoxel_y), float(sVoxel_z), float(center_x), float(center_y), float(center_z),
+            _ptr(means3D), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(radii_x),
+            _ptr(radii_y), _ptr(radii_z), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+            scratch.data_ptr(), _ptr(dL), _ptr(g_op), _ptr(g_mean), _ptr(g_cov), _ptr(g_scale), _ptr(g_rot),
+            int(bool(debug)))
+        check(rc, "r2x_voxel_backward")
+    return g_op, g_mean, g_cov, g_scale, g_rot

@@ -1,0 +1,363 @@
+// r2x_binning.cu -- see r2x_binning.cuh for the design.
+#include "r2x_binning.cuh"
+
+namespace r2x {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t binning_bytes(long long R) {
+    size_t r = (size_t)(R > 0 ? R : 1);
+    size_t per = align_up(r * sizeof(uint32_t), 256);
+    return 7 * per + align_up(256 * SORT_MAX_BLOCKS * sizeof(uint32_t), 256) + 256;
+}
+
+BinningView binning_view(void* buf, long long R) {
+    BinningView v;
+    size_t r = (size_t)(R > 0 ? R : 1);
+    size_t per = align_up(r * sizeof(uint32_t), 256);
+    char* p = (char*)align_up((size_t)buf, 256);
+    v.keys[0] = (uint32_t*)p; p += per;
+    v.keys[1] = (uint32_t*)p; p += per;
+    v.vals[0] = (uint32_t*)p; p += per;
+    v.vals[1] = (uint32_t*)p; p += per;
+    v.inst_g = (uint32_t*)p; p += per;
+    v.point_list = (uint32_t*)p; p += per;
+    v.inst_pos = (uint32_t*)p; p += per;
+    v.hist = (uint32_t*)p;
+    v.capacity = R;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass inclusive scan (decoupled look-back), 1024 items per CTA.
+// state[0] = ticket counter; state[1 + b] = (flag << 62) | value, flag 1 = aggregate, 2 = inclusive.
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+size_t scan_state_bytes(int P) { return sizeof(unsigned long long) * (size_t)(2 + (P + SCAN_TILE - 1) / SCAN_TILE); }
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_t* __restrict__ in,
+                                                            uint32_t* __restrict__ out,
+                                                            unsigned long long* state, uint32_t* d_total,
+                                                            int nblocks) {
+    __shared__ uint32_t s_bid;
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = (uint32_t)atomicAdd(&state[0], 1ull);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    volatile unsigned long long* st = state + 1;
+
+    const int base = bid * SCAN_TILE + tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= P && ((size_t)(in + base) & 15) == 0) {
+        uint4 q = *reinterpret_cast<const uint4*>(in + base);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < P) ? in[base + k] : 0u;
+    }
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { tsum += v[k]; v[k] = tsum; }
+    // warp inclusive scan of thread sums
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wpre = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        uint32_t t = s_warp[w];
+        if (w < warp) wpre += t;
+        agg += t;
+    }
+    if (tid == 0) {
+        unsigned long long excl = 0;
+        if (bid == 0) {
+            st[0] = (2ull << 62) | (unsigned long long)agg;
+        } else {
+            st[bid] = (1ull << 62) | (unsigned long long)agg;
+            __threadfence();
+            int p = (int)bid - 1;
+            while (true) {
+                unsigned long long s = st[p];
+                unsigned long long flag = s >> 62;
+                if (flag == 0) continue;
+                excl += s & ((1ull << 62) - 1);
+                if (flag == 2) break;
+                --p;
+            }
+            st[bid] = (2ull << 62) | (excl + agg);
+        }
+        __threadfence();
+        s_excl = excl;
+        if ((int)bid == nblocks - 1) *d_total = (uint32_t)(excl + agg);
+    }
+    __syncthreads();
+    const uint32_t off = (uint32_t)s_excl + wpre + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < P) out[base + k] = off + v[k];
+}
+
+int launch_scan(cudaStream_t st, int P, const uint32_t* tiles_touched, uint32_t* offsets, void* scan_state,
+                uint32_t* d_total) {
+    const int nb = (P + SCAN_TILE - 1) / SCAN_TILE;
+    R2X_CUDA_OK(cudaMemsetAsync(scan_state, 0, scan_state_bytes(P), st));
+    scan_kernel<<<nb, SCAN_THREADS, 0, st>>>(P, tiles_touched, offsets, (unsigned long long*)scan_state, d_total, nb);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Instance emission: one warp per 32 Gaussians, each covered Gaussian's tiles written by all lanes
+// (coalesced).  Order == reference duplicateWithKeys: Gaussian ascending, then z, y, x ascending.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) emit_kernel(int P, const uint16_t* __restrict__ cube,
+                                                   const uint32_t* __restrict__ tiles_touched,
+                                                   const uint32_t* __restrict__ offsets, int gx, int gy,
+                                                   long long capacity, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ inst_g) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t n = 0, start = 0, c01 = 0, c23 = 0, c45 = 0;
+    if (g < P) {
+        n = tiles_touched[g];
+        if (n) {
+            start = offsets[g] - n;
+            const uint32_t* c = reinterpret_cast<const uint32_t*>(cube + 6 * (size_t)g);
+            c01 = c[0]; c23 = c[1]; c45 = c[2];
+        }
+    }
+    uint32_t live = __ballot_sync(0xffffffffu, n != 0);
+    while (live) {
+        const int src = __ffs(live) - 1;
+        live &= live - 1;
+        const uint32_t n_s = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t st_s = __shfl_sync(0xffffffffu, start, src);
+        const uint32_t a = __shfl_sync(0xffffffffu, c01, src);
+        const uint32_t b = __shfl_sync(0xffffffffu, c23, src);
+        const uint32_t c = __shfl_sync(0xffffffffu, c45, src);
+        const uint32_t x0 = a & 0xffff, y0 = a >> 16, z0 = b & 0xffff, x1 = b >> 16, y1 = c & 0xffff;
+        const uint32_t w = x1 - x0, h = y1 - y0, wh = w * h;
+        const uint32_t gid = (uint32_t)(g - lane + src);
+        for (uint32_t k = lane; k < n_s; k += 32) {
+            const uint32_t z = k / wh, r = k - z * wh, y = r / w, x = r - y * w;
+            const uint32_t tile = ((z0 + z) * (uint32_t)gy + (y0 + y)) * (uint32_t)gx + (x0 + x);
+            const long long o = (long long)st_s + k;
+            if (o < capacity) { keys[o] = tile; inst_g[o] = gid; }
+        }
+    }
+}
+
+int launch_emit(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched,
+                const uint32_t* offsets, int gx, int gy, const uint32_t* d_total, const BinningView& bv) {
+    (void)d_total;
+    if (P <= 0) return 0;
+    emit_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, cube, tiles_touched, offsets, gx, gy, bv.capacity, bv.keys[0], bv.inst_g);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort, 8 bits per pass: per-CTA digit histogram -> exclusive scan of the
+// digit-major [256 x nb] table -> stable scatter.  Each CTA owns a contiguous range of instances
+// (a multiple of SORT_CHUNK) and walks it in order, so order among equal digits is preserved.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long per_block_items(long long R, int nb) {
+    long long per = (R + nb - 1) / nb;
+    return (per + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t* __restrict__ keys,
+                                                                 const uint32_t* __restrict__ d_total,
+                                                                 long long capacity, int shift, int nb,
+                                                                 uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[256];
+    long long R = *d_total;
+    if (R > capacity) R = capacity;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long per = per_block_items(R, nb);
+    const long long lo = per * blockIdx.x;
+    long long hi = lo + per;
+    if (hi > R) hi = R;
+    for (long long i = lo + threadIdx.x; i < hi; i += SORT_THREADS) atomicAdd(&s_h[(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// exclusive scan of n = 256*nb uint32 in place, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int n) {
+    __shared__ uint32_t s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int lo = tid * per;
+    const int hi = min(lo + per, n);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += hist[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        uint32_t t = hist[i];
+        hist[i] = run;
+        run += t;
+    }
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ inst_g, uint32_t* __restrict__ point_list,
+    uint32_t* __restrict__ inst_pos, const uint32_t* __restrict__ d_total, long long capacity, int shift, int nb,
+    const uint32_t* __restrict__ hist) {
+    constexpr int NW = SORT_THREADS / 32;
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_wcnt[NW][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long R = *d_total;
+    if (R > capacity) R = capacity;
+    const long long per = per_block_items(R, nb);
+    const long long lo = per * blockIdx.x;
+    long long hi = lo + per;
+    if (hi > R) hi = R;
+    s_base[tid] = hist[(size_t)tid * nb + blockIdx.x];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (long long cb = lo; cb < hi; cb += SORT_CHUNK) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s_wcnt[w][tid] = 0;
+        __syncthreads();
+        uint32_t key[SORT_ITEMS];
+        uint32_t rnk[SORT_ITEMS];
+        const long long wbase = cb + (long long)warp * (32 * SORT_ITEMS);
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const long long i = wbase + k * 32 + lane;
+            const bool valid = i < hi;
+            key[k] = valid ? keys_in[i] : 0u;
+            const uint32_t d = valid ? ((key[k] >> shift) & 255u) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = s_wcnt[warp][d];
+                s_wcnt[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rnk[k] = old + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // per-digit exclusive prefix over warps (thread == digit)
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t t = s_wcnt[w][tid];
+                s_wcnt[w][tid] = run;
+                run += t;
+            }
+            __syncthreads();
+            // scatter
+#pragma unroll
+            for (int k = 0; k < SORT_ITEMS; ++k) {
+                const long long i = wbase + k * 32 + lane;
+                if (i < hi) {
+                    const uint32_t d = (key[k] >> shift) & 255u;
+                    const uint32_t pos = s_base[d] + s_wcnt[warp][d] + rnk[k];
+                    const uint32_t v = FIRST ? (uint32_t)i : vals_in[i];
+                    keys_out[pos] = key[k];
+                    if (LAST) {
+                        point_list[pos] = inst_g[v];
+                        inst_pos[v] = pos;
+                    } else {
+                        vals_out[pos] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            s_base[tid] += run;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ d_total,
+                                                          long long capacity, uint2* __restrict__ ranges) {
+    long long R = *d_total;
+    if (R > capacity) R = capacity;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        const uint32_t cur = keys[i];
+        if (i == 0) ranges[cur].x = 0;
+        else {
+            const uint32_t prev = keys[i - 1];
+            if (cur != prev) { ranges[prev].y = (uint32_t)i; ranges[cur].x = (uint32_t)i; }
+        }
+        if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    }
+}
+
+int launch_sort_and_ranges(cudaStream_t st, long long R_launch, int num_tiles, const uint32_t* d_total,
+                           const BinningView& bv, uint2* ranges, uint32_t** sorted_keys_out) {
+    R2X_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, st));
+    if (sorted_keys_out) *sorted_keys_out = bv.keys[0];
+    if (R_launch <= 0) return 0;
+    int bits = 1;
+    while ((1ll << bits) < (long long)num_tiles) ++bits;
+    const int passes = (bits + 7) / 8;
+    long long nbl = (R_launch + SORT_CHUNK - 1) / SORT_CHUNK;
+    const int nb = (int)(nbl < SORT_MAX_BLOCKS ? nbl : SORT_MAX_BLOCKS);
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        const bool first = (p == 0), last = (p == passes - 1);
+        sort_hist_kernel<<<nb, SORT_THREADS, 0, st>>>(bv.keys[cur], d_total, bv.capacity, shift, nb, bv.hist);
+        sort_scan_kernel<<<1, 1024, 0, st>>>(bv.hist, 256 * nb);
+#define R2X_SCATTER(F, L)                                                                                          \
+    sort_scatter_kernel<F, L><<<nb, SORT_THREADS, 0, st>>>(bv.keys[cur], bv.vals[cur], bv.keys[cur ^ 1],           \
+                                                           bv.vals[cur ^ 1], bv.inst_g, bv.point_list, bv.inst_pos, \
+                                                           d_total, bv.capacity, shift, nb, bv.hist)
+        if (first && last) R2X_SCATTER(true, true);
+        else if (first) R2X_SCATTER(true, false);
+        else if (last) R2X_SCATTER(false, true);
+        else R2X_SCATTER(false, false);
+#undef R2X_SCATTER
+        R2X_CUDA_OK(cudaGetLastError());
+        cur ^= 1;
+    }
+    if (sorted_keys_out) *sorted_keys_out = bv.keys[cur];
+    long long nbr = (R_launch + 255) / 256;
+    const int gr = (int)(nbr < 148 * 8 ? nbr : 148 * 8);
+    tile_ranges_kernel<<<gr, 256, 0, st>>>(bv.keys[cur], d_total, bv.capacity, ranges);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace r2x

@@ -1,0 +1,57 @@
+// r2x_binning.cuh -- tile binning shared by the rasterizer (2-D, 16x16 tiles) and the voxelizer
+// (3-D, 8x8x8 tiles): prefix sum over tiles_touched, instance emission, a STABLE least-significant-
+// digit radix sort of the instances by tile id only, and per-tile ranges.
+//
+// Replaces (reference): cub::DeviceScan::InclusiveSum + blocking D2H (RAS/rasterizer_impl.cu:275-279),
+// duplicateWithKeys (:70-111), cub::DeviceRadixSort::SortPairs on 64-bit (tile|depth) keys (:298-306),
+// identifyTileRanges (:116-138) -- and the 3-D copies in VOX/voxelizer_impl.cu:54-128,244-283.
+//
+// Design: X-ray accumulation is order-free, so the depth half of the reference key is never sorted on.
+// Instances are emitted in the reference's order (Gaussian index ascending, tiles row-major inside the
+// bounding rectangle) and moved by a stable sort keyed on the tile id alone (ceil(log2 T) bits ->
+// 2 passes of 8 bits for 1024 or 32768 tiles, instead of 6 passes over 64-bit keys).  Stability makes
+// every per-tile list ascending in Gaussian index: the render order -- and with it every float sum in
+// the forward and backward pass -- is a deterministic function of the inputs.  The reference's
+// 64-bit key of an instance is (tile_id << 32) | float_bits(depth[gaussian]); r2x_*_export_keys
+// reconstructs it from the sorted list for the bit-exact parity tests.
+#pragma once
+#include "r2x_common.cuh"
+
+namespace r2x {
+
+struct BinningView {
+    // all device pointers, carved out of the caller's binning buffer
+    uint32_t* keys[2];     // tile id per instance, ping-pong
+    uint32_t* vals[2];     // original instance index, ping-pong
+    uint32_t* inst_g;      // [R] Gaussian id of instance i (emission order)
+    uint32_t* point_list;  // [R] Gaussian id at sorted position s
+    uint32_t* inst_pos;    // [R] sorted position of original instance i
+    uint32_t* hist;        // [256 * SORT_MAX_BLOCKS] digit-major per-block histograms
+    long long capacity;    // instances the buffer can hold
+};
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                         // keys per thread per sub-chunk
+constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096
+constexpr int SORT_MAX_BLOCKS = 296;                   // 2 CTAs per SM on 148 SMs
+
+size_t binning_bytes(long long R);
+BinningView binning_view(void* buf, long long R);
+
+// Exclusive->inclusive scan of tiles_touched[P] into offsets[P]; total (R) is written to *d_total
+// (device) -- single pass, decoupled look-back.  scan_state needs scan_state_bytes(P) bytes, zeroed
+// by the call itself.
+size_t scan_state_bytes(int P);
+int launch_scan(cudaStream_t st, int P, const uint32_t* tiles_touched, uint32_t* offsets, void* scan_state,
+                uint32_t* d_total);
+
+// cube: 6 x uint16 per Gaussian (x0,y0,z0,x1,y1,z1); 2-D uses z0=0,z1=1.
+int launch_emit(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched,
+                const uint32_t* offsets, int gx, int gy, const uint32_t* d_total, const BinningView& bv);
+
+// Stable sort by tile id + per-tile ranges.  `R_launch` sizes the grids (R itself is read on the device
+// from d_total so that the same launch sequence works when the host does not know R).
+int launch_sort_and_ranges(cudaStream_t st, long long R_launch, int num_tiles, const uint32_t* d_total,
+                           const BinningView& bv, uint2* ranges, uint32_t** sorted_keys_out);
+
+}  // namespace r2x

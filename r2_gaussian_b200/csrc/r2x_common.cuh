@@ -1,0 +1,171 @@
+// r2x_common.cuh -- shared device helpers for the sm_100a X-ray Gaussian kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define R2X_TILE 16     // detector tile edge, pixels   (reference RAS/config.h:16-17)
+#define R2X_VTILE 8     // voxel tile edge              (reference VOX/config.h:16-18)
+
+#define R2X_CUDA_OK(expr)                                                      \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return r2x::fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+namespace r2x {
+
+int fail(cudaError_t e, const char* what, const char* file, int line);
+int fail_msg(int code, const char* msg);
+
+// ---------------------------------------------------------------------------------------------
+// Exactly-rounded float32 building blocks.  The reference's radii / tile rectangles / depth bits
+// must be reproduced bit for bit, so every operation on that path is written with an explicit
+// rounding intrinsic: the compiler can neither fuse nor re-associate them.  The sequence mirrors
+// the FMA contraction nvcc chose for the reference's own expressions.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+// a0*b0 + a1*b1 + a2*b2  ==  fma(a2,b2, fma(a0,b0, rn(a1*b1)))
+__device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return ffma(a2, b2, ffma(a0, b0, fmul(a1, b1)));
+}
+// row r of a column-major-flat 4x4 applied to (x,y,z,1)
+__device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {
+    return fadd(m[12 + r], ffma(z, m[8 + r], ffma(x, m[r], fmul(y, m[4 + r]))));
+}
+
+// Sigma = (S R)^T (S R) from scale*mod and the un-normalised quaternion (r,x,y,z);
+// six floats (S00,S01,S02,S11,S12,S22).
+__device__ __forceinline__ void cov3d_from_scale_rot(float s0, float s1, float s2, float mod, float4 q, float* cov) {
+    const float sx = fmul(mod, s0), sy = fmul(mod, s1), sz = fmul(mod, s2);
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float yy = fmul(y, y), zz = fmul(z, z);
+    const float xy = fmul(x, y), rz = fmul(r, z), xz = fmul(x, z), ry = fmul(r, y), yz = fmul(y, z), rx = fmul(r, x);
+    const float yy_zz = fadd(yy, zz);
+    const float xx_zz = ffma(x, x, zz);
+    const float xx_yy = ffma(x, x, yy);
+    const float a01 = fsub(xy, rz), a02 = fadd(ry, xz), a10 = fadd(xy, rz);
+    const float a12 = fsub(yz, rx), a20 = fsub(xz, ry), a21 = fadd(rx, yz);
+    const float R00 = fsub(1.0f, fadd(yy_zz, yy_zz));
+    const float R01 = fadd(a01, a01), R02 = fadd(a02, a02), R10 = fadd(a10, a10);
+    const float R11 = fsub(1.0f, fadd(xx_zz, xx_zz));
+    const float R12 = fadd(a12, a12), R20 = fadd(a20, a20), R21 = fadd(a21, a21);
+    const float R22 = fsub(1.0f, fadd(xx_yy, xx_yy));
+    const float M00 = fmul(sx, R00), M01 = fmul(sy, R01), M02 = fmul(sz, R02);
+    const float M10 = fmul(sx, R10), M11 = fmul(sy, R11), M12 = fmul(sz, R12);
+    const float M20 = fmul(sx, R20), M21 = fmul(sy, R21), M22 = fmul(sz, R22);
+    cov[0] = dot3c(M00, M00, M01, M01, M02, M02);
+    cov[1] = dot3c(M10, M00, M11, M01, M12, M02);
+    cov[2] = dot3c(M20, M00, M21, M01, M22, M02);
+    cov[3] = dot3c(M10, M10, M11, M11, M12, M12);
+    cov[4] = dot3c(M20, M10, M21, M11, M22, M12);
+    cov[5] = dot3c(M20, M20, M21, M21, M22, M22);
+}
+
+// Gradient of Sigma = (S R)^T (S R) w.r.t. scale (3) and the raw quaternion (4) given dL/dSigma (6,
+// off-diagonals counted once).  Plain float math (tolerance territory, not bit-exact).
+__device__ __forceinline__ void cov3d_backward(float s0, float s1, float s2, float mod, float4 q,
+                                               const float* dS6, float* dscale, float* drot) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    // Rc[c][k]: glm column c, row k (textual rows of the rotation matrix)
+    const float Rc[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                            {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                            {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+    const float s[3] = {mod * s0, mod * s1, mod * s2};
+    const float dS[3][3] = {{dS6[0], 0.5f * dS6[1], 0.5f * dS6[2]},
+                            {0.5f * dS6[1], dS6[3], 0.5f * dS6[4]},
+                            {0.5f * dS6[2], 0.5f * dS6[4], dS6[5]}};
+    float dMt[3][3];  // dMt[k][c] = dL/dM[c][k],  M[c][k] = s_k * Rc[c][k]
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            dMt[k][c] = (2.0f * s[k] * Rc[0][k]) * dS[c][0] + (2.0f * s[k] * Rc[1][k]) * dS[c][1] +
+                        (2.0f * s[k] * Rc[2][k]) * dS[c][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dscale[k] = Rc[0][k] * dMt[k][0] + Rc[1][k] * dMt[k][1] + Rc[2][k] * dMt[k][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dMt[k][c] *= s[k];
+    drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+    drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) -
+              4 * x * (dMt[2][2] + dMt[1][1]);
+    drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) -
+              4 * y * (dMt[2][2] + dMt[0][0]);
+    drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
+              4 * z * (dMt[1][1] + dMt[0][0]);
+}
+
+// dL/dSigma3 (6) += J^T-style pull-back of dL/dhat (6) through hat = Mm^T V Mm, Mm[c*3+r].
+__device__ __forceinline__ void dcov3d_from_dhat(const float* Mm, const float* dh, float* dcov) {
+#define M_(c, r) Mm[(c) * 3 + (r)]
+    const float da = dh[0], db = dh[1], dc = dh[2], dd = dh[3], de = dh[4], df = dh[5];
+    dcov[0] += M_(0,0)*M_(0,0)*da + M_(0,0)*M_(1,0)*db + M_(0,0)*M_(2,0)*dc + M_(1,0)*M_(1,0)*dd + M_(1,0)*M_(2,0)*de + M_(2,0)*M_(2,0)*df;
+    dcov[3] += M_(0,1)*M_(0,1)*da + M_(0,1)*M_(1,1)*db + M_(0,1)*M_(2,1)*dc + M_(1,1)*M_(1,1)*dd + M_(1,1)*M_(2,1)*de + M_(2,1)*M_(2,1)*df;
+    dcov[5] += M_(0,2)*M_(0,2)*da + M_(0,2)*M_(1,2)*db + M_(0,2)*M_(2,2)*dc + M_(1,2)*M_(1,2)*dd + M_(1,2)*M_(2,2)*de + M_(2,2)*M_(2,2)*df;
+    dcov[1] += 2*M_(0,0)*M_(0,1)*da + (M_(0,1)*M_(1,0)+M_(0,0)*M_(1,1))*db + (M_(0,1)*M_(2,0)+M_(0,0)*M_(2,1))*dc + 2*M_(1,0)*M_(1,1)*dd + (M_(1,1)*M_(2,0)+M_(1,0)*M_(2,1))*de + 2*M_(2,0)*M_(2,1)*df;
+    dcov[2] += 2*M_(0,0)*M_(0,2)*da + (M_(0,2)*M_(1,0)+M_(0,0)*M_(1,2))*db + (M_(0,2)*M_(2,0)+M_(0,0)*M_(2,2))*dc + 2*M_(1,0)*M_(1,2)*dd + (M_(1,2)*M_(2,0)+M_(1,0)*M_(2,2))*de + 2*M_(2,0)*M_(2,2)*df;
+    dcov[4] += 2*M_(0,1)*M_(0,2)*da + (M_(0,2)*M_(1,1)+M_(0,1)*M_(1,2))*db + (M_(0,2)*M_(2,1)+M_(0,1)*M_(2,2))*dc + 2*M_(1,1)*M_(1,2)*dd + (M_(1,2)*M_(2,1)+M_(1,1)*M_(2,2))*de + 2*M_(2,1)*M_(2,2)*df;
+#undef M_
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier helpers.  SASS: UBLKCP / SYNCS.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 16-byte Ampere-style async gather (LDGSTS): per-thread source address.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+}  // namespace r2x

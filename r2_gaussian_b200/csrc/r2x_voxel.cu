@@ -1,0 +1,468 @@
+// r2x_voxel.cu -- density-volume (3-D voxelizer) kernels for sm_100a.
+//
+// Replaces the reference's VOX/forward.cu (preprocessCUDA :58-178, renderCUDA :183-315) and
+// VOX/backward.cu (renderCUDA :216-374, computeCov3DCUDA :86-177, preprocessCUDA :180-213).
+//
+// Same machinery as r2x_raster.cu with 8x8x8 tiles:
+//   voxel_preprocess_kernel  per Gaussian, TMA-staged parameters, bit-exact radii / cube / tiles_touched.
+//   voxel_render_kernel      one CTA per tile, 256 threads = 4 list slices x 64 (x,y) columns; each thread
+//                            owns the 8 voxels of a z column (contiguous in memory): the x/y part of the
+//                            quadratic form is computed once per Gaussian and column.
+//   voxel_render_bwd_kernel  one thread per (tile, Gaussian) instance, loops over the 512 voxels and keeps
+//                            the ten weighted moments in registers; no atomics.
+//   voxel_gauss_bwd_kernel   per Gaussian: fixed-order sum of instance moments + chain rule.
+#include "r2x_voxel.cuh"
+
+namespace r2x {
+
+static constexpr float LOG2E = 1.4426950408889634f;
+
+struct VoxCov {
+    float a, b, c, d, e, f;  // covariance in voxel units
+    float det;
+};
+
+// hat = D Sigma D with D = diag(1/dVoxel) and its determinant; bit-exact restatement of the dataflow
+// nvcc produced for VOX/forward.cu:110-125.
+__device__ __forceinline__ VoxCov voxel_cov(const float* c3, float ix, float iy, float iz) {
+    VoxCov v;
+    v.a = fmul(fmul(ix, c3[0]), ix);
+    v.b = fmul(fmul(iy, c3[1]), ix);
+    v.c = fmul(fmul(iz, c3[2]), ix);
+    v.d = fmul(fmul(iy, c3[3]), iy);
+    v.e = fmul(fmul(iz, c3[4]), iy);
+    v.f = fmul(fmul(iz, c3[5]), iz);
+    const float ad = fmul(v.a, v.d), ae = fmul(v.a, v.e), bf = fmul(v.b, v.f), cd = fmul(v.c, v.d);
+    float det = fmul(ad, v.f);
+    det = ffma(fmul(fadd(v.b, v.b), v.c), v.e, det);
+    det = fsub(det, fmul(v.e, ae));
+    det = fsub(det, fmul(v.b, bf));
+    det = fsub(det, fmul(v.c, cd));
+    v.det = det;
+    return v;
+}
+
+__device__ __forceinline__ void voxel_inverse(const VoxCov& v, float* inv) {
+    const float di = frcp(v.det);
+    const float ad = fmul(v.a, v.d), ae = fmul(v.a, v.e), bf = fmul(v.b, v.f), cd = fmul(v.c, v.d);
+    inv[0] = fmul(fsub(fmul(v.d, v.f), fmul(v.e, v.e)), di);
+    inv[1] = fmul(fsub(fmul(v.c, v.e), bf), di);
+    inv[2] = fmul(fsub(fmul(v.b, v.e), cd), di);
+    inv[3] = fmul(fsub(fmul(v.a, v.f), fmul(v.c, v.c)), di);
+    inv[4] = fmul(fsub(fmul(v.b, v.c), ae), di);
+    inv[5] = fmul(fsub(ad, fmul(v.b, v.b)), di);
+}
+
+constexpr int VPRE_THREADS = 256;
+
+__global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
+    int P, const float* __restrict__ means, const float* __restrict__ scales, float scale_modifier,
+    const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ cov3D_precomp,
+    VoxelGrid vg, int use_tma, int* __restrict__ radii_x, int* __restrict__ radii_y, int* __restrict__ radii_z,
+    VoxelGeom geom) {
+    __shared__ __align__(16) float s_means[VPRE_THREADS * 3];
+    __shared__ __align__(16) float s_scales[VPRE_THREADS * 3];
+    __shared__ __align__(16) float4 s_rots[VPRE_THREADS];
+    __shared__ __align__(16) float s_opac[VPRE_THREADS];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * VPRE_THREADS;
+    const int g = base + tid;
+    const bool full = (base + VPRE_THREADS <= P);
+    const bool tma = use_tma && full;
+    if (tma && tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&s_bar, VPRE_THREADS * (12 + 4 + 12 + 16));
+        tma_load_1d(s_means, means + (size_t)base * 3, VPRE_THREADS * 12, &s_bar);
+        tma_load_1d(s_opac, opac + base, VPRE_THREADS * 4, &s_bar);
+        tma_load_1d(s_scales, scales + (size_t)base * 3, VPRE_THREADS * 12, &s_bar);
+        tma_load_1d(s_rots, rots + (size_t)base * 4, VPRE_THREADS * 16, &s_bar);
+    }
+    __syncthreads();
+    if (tma) mbar_wait(&s_bar, 0);
+    if (g >= P) return;
+
+    float mx, my, mz, s0, s1, s2, rho;
+    float4 q;
+    if (tma) {
+        mx = s_means[3 * tid]; my = s_means[3 * tid + 1]; mz = s_means[3 * tid + 2];
+        rho = s_opac[tid];
+        s0 = s_scales[3 * tid]; s1 = s_scales[3 * tid + 1]; s2 = s_scales[3 * tid + 2];
+        q = s_rots[tid];
+    } else {
+        mx = means[3 * (size_t)g]; my = means[3 * (size_t)g + 1]; mz = means[3 * (size_t)g + 2];
+        rho = opac[g];
+        // the reference reads scales unconditionally (VOX/forward.cu:137): the radius needs them even
+        // when a precomputed covariance is supplied
+        s0 = scales[3 * (size_t)g]; s1 = scales[3 * (size_t)g + 1]; s2 = scales[3 * (size_t)g + 2];
+        q = rots ? make_float4(rots[4 * (size_t)g], rots[4 * (size_t)g + 1], rots[4 * (size_t)g + 2], rots[4 * (size_t)g + 3])
+                 : make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    int rxi = 0, ryi = 0, rzi = 0;
+    uint32_t ntiles = 0, c01 = 0, c23 = 0, c45 = 0;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+
+    float c3[6];
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c3[k] = cov3D_precomp[6 * (size_t)g + k];
+    } else {
+        cov3d_from_scale_rot(s0, s1, s2, scale_modifier, q, c3);
+    }
+    const VoxCov vc = voxel_cov(c3, vg.ix, vg.iy, vg.iz);
+    if (vc.det != 0.0f) {
+        float inv[6];
+        voxel_inverse(vc, inv);
+        const float ms3 = fmul(fmaxf(fmaxf(s0, s1), s2), 3.0f);
+        const float rx = ceilf(fdiv(ms3, vg.dvx)), ry = ceilf(fdiv(ms3, vg.dvy)), rz = ceilf(fdiv(ms3, vg.dvz));
+        const float pvx = fdiv(ffma(vg.sx, 0.5f, fsub(mx, vg.cx)), vg.dvx);
+        const float pvy = fdiv(ffma(vg.sy, 0.5f, fsub(my, vg.cy)), vg.dvy);
+        const float pvz = fdiv(ffma(vg.sz, 0.5f, fsub(mz, vg.cz)), vg.dvz);
+        const float hx = fadd(pvx, rx), hy = fadd(pvy, ry), hz = fadd(pvz, rz);
+        const float lx = fsub(pvx, rx), ly = fsub(pvy, ry), lz = fsub(pvz, rz);
+        const bool outside = (hx < 0.f) || (hy < 0.f) || (hz < 0.f) || (lx > (float)vg.nx) || (ly > (float)vg.ny) ||
+                             (lz > (float)vg.nz);
+        if (!outside) {
+            const int x0 = min(vg.gx, max(0, (int)fmul(lx, 0.125f)));
+            const int y0 = min(vg.gy, max(0, (int)fmul(ly, 0.125f)));
+            const int z0 = min(vg.gz, max(0, (int)fmul(lz, 0.125f)));
+            const int x1 = min(vg.gx, max(0, (int)fmul(fadd(fadd(hx, 8.0f), -1.0f), 0.125f)));
+            const int y1 = min(vg.gy, max(0, (int)fmul(fadd(fadd(hy, 8.0f), -1.0f), 0.125f)));
+            const int z1 = min(vg.gz, max(0, (int)fmul(fadd(fadd(hz, 8.0f), -1.0f), 0.125f)));
+            const int nt = (x1 - x0) * (y1 - y0) * (z1 - z0);
+            if (nt != 0) {
+                rxi = (int)rx; ryi = (int)ry; rzi = (int)rz;
+                ntiles = (uint32_t)nt;
+                r0 = make_float4(pvx, pvy, pvz, rho);
+                r1 = make_float4(inv[0] * (-0.5f * LOG2E), inv[1] * (-LOG2E), inv[2] * (-LOG2E), inv[3] * (-0.5f * LOG2E));
+                r2 = make_float4(inv[4] * (-LOG2E), inv[5] * (-0.5f * LOG2E), mz, 0.f);
+                c01 = (uint32_t)x0 | ((uint32_t)y0 << 16);
+                c23 = (uint32_t)z0 | ((uint32_t)x1 << 16);
+                c45 = (uint32_t)y1 | ((uint32_t)z1 << 16);
+            }
+        }
+    }
+    radii_x[g] = rxi; radii_y[g] = ryi; radii_z[g] = rzi;
+    geom.tiles_touched[g] = ntiles;
+    geom.rec[4 * (size_t)g + 0] = r0;
+    geom.rec[4 * (size_t)g + 1] = r1;
+    geom.rec[4 * (size_t)g + 2] = r2;
+    uint32_t* cu = reinterpret_cast<uint32_t*>(geom.cube + 6 * (size_t)g);
+    cu[0] = c01; cu[1] = c23; cu[2] = c45;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward render
+// ------------------------------------------------------------------------------------------------
+constexpr int VR_THREADS = 256;
+constexpr int VR_BATCH = 256;
+constexpr int VR_SLICES = 4;
+
+__global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
+                                                                  const uint32_t* __restrict__ point_list,
+                                                                  const float4* __restrict__ rec,
+                                                                  float* __restrict__ out_volume) {
+    __shared__ __align__(16) float4 s_rec[2][VR_BATCH][3];       // 24 KB
+    __shared__ __align__(16) float s_red[VR_SLICES - 1][64][8];  // 6 KB
+
+    const int tid = threadIdx.x;
+    const int slice = tid >> 6, q = tid & 63;
+    const int lx = q >> 3, ly = q & 7;
+    const int tile = blockIdx.x;
+    const int tx = tile % vg.gx, ty = (tile / vg.gx) % vg.gy, tz = tile / (vg.gx * vg.gy);
+    const float fx = (float)(tx * R2X_VTILE + lx) + 0.5f;
+    const float fy = (float)(ty * R2X_VTILE + ly) + 0.5f;
+    const float fz0 = (float)(tz * R2X_VTILE) + 0.5f;
+
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+    const int nbatches = (n + VR_BATCH - 1) / VR_BATCH;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+
+    uint32_t id_next = 0;
+    if (tid < n) id_next = point_list[range.x + tid];
+    if (nbatches > 0) {
+        if (tid < n) {
+            cp_async16(&s_rec[0][tid][0], &rec[4 * (size_t)id_next]);
+            cp_async16(&s_rec[0][tid][1], &rec[4 * (size_t)id_next + 1]);
+            cp_async16(&s_rec[0][tid][2], &rec[4 * (size_t)id_next + 2]);
+        }
+        cp_async_commit();
+        if (VR_BATCH + tid < n) id_next = point_list[range.x + VR_BATCH + tid];
+    }
+    for (int b = 0; b < nbatches; ++b) {
+        const int stage = b & 1;
+        if (b + 1 < nbatches) {
+            const int i1 = (b + 1) * VR_BATCH + tid;
+            if (i1 < n) {
+                cp_async16(&s_rec[stage ^ 1][tid][0], &rec[4 * (size_t)id_next]);
+                cp_async16(&s_rec[stage ^ 1][tid][1], &rec[4 * (size_t)id_next + 1]);
+                cp_async16(&s_rec[stage ^ 1][tid][2], &rec[4 * (size_t)id_next + 2]);
+            }
+            cp_async_commit();
+            const int i2 = (b + 2) * VR_BATCH + tid;
+            if (i2 < n) id_next = point_list[range.x + i2];
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int nb = min(VR_BATCH, n - b * VR_BATCH);
+#pragma unroll 2
+        for (int j = slice; j < nb; j += VR_SLICES) {
+            const float4 r0 = s_rec[stage][j][0];  // px,py,pz,rho
+            const float4 r1 = s_rec[stage][j][1];  // a2,b2,c2,d2
+            const float4 r2 = s_rec[stage][j][2];  // e2,f2,depth,-
+            const float dx = r0.x - fx, dy = r0.y - fy;
+            const float q0 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), (r1.w * dy) * dy);
+            const float lin = fmaf(r1.z, dx, r2.x * dy);
+            const float dz0 = r0.z - fz0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float dz = dz0 - (float)k;
+                const float u = fmaf(r2.y, dz, lin);
+                const float p = fmaf(dz, u, q0);  // = power * log2(e)
+                const float al = r0.w * ex2_approx(p);
+                if (!(p > 0.0f) && !(al < 0.000001f)) acc[k] += al;
+            }
+        }
+        __syncthreads();
+    }
+    if (slice > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_red[slice - 1][q][k] = acc[k];
+    }
+    __syncthreads();
+    if (slice == 0) {
+        const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z0 = tz * R2X_VTILE;
+        if (x < vg.nx && y < vg.ny) {
+            float* dst = out_volume + ((size_t)x * vg.ny + y) * vg.nz + z0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float v = acc[k];
+                v += s_red[0][q][k];
+                v += s_red[1][q][k];
+                v += s_red[2][q][k];
+                if (z0 + k < vg.nz) dst[k] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward render: thread = instance; moments S0, Sx,Sy,Sz, Sxx,Sxy,Sxz,Syy,Syz,Szz of t = dL*G
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
+                                                               const uint32_t* __restrict__ point_list,
+                                                               const float4* __restrict__ rec,
+                                                               const float* __restrict__ dL_dvol,
+                                                               float4* __restrict__ inst_grad) {
+    __shared__ __align__(16) float s_dl[R2X_VTILE][R2X_VTILE][R2X_VTILE];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tx = tile % vg.gx, ty = (tile / vg.gx) % vg.gy, tz = tile / (vg.gx * vg.gy);
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+    if (n == 0) return;
+    for (int v = tid; v < 512; v += 256) {
+        const int lz = v & 7, ly = (v >> 3) & 7, lx = v >> 6;
+        const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z = tz * R2X_VTILE + lz;
+        s_dl[lx][ly][lz] = (x < vg.nx && y < vg.ny && z < vg.nz) ? dL_dvol[((size_t)x * vg.ny + y) * vg.nz + z] : 0.f;
+    }
+    __syncthreads();
+    const float fx0 = (float)(tx * R2X_VTILE) + 0.5f, fy0 = (float)(ty * R2X_VTILE) + 0.5f,
+                fz0 = (float)(tz * R2X_VTILE) + 0.5f;
+    for (int i = tid; i < n; i += 256) {
+        const uint32_t s = range.x + i;
+        const uint32_t g = point_list[s];
+        const float4 r0 = rec[4 * (size_t)g];
+        const float4 r1 = rec[4 * (size_t)g + 1];
+        const float4 r2 = rec[4 * (size_t)g + 2];
+        float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
+        const float dz0 = r0.z - fz0;
+#pragma unroll 1
+        for (int ix = 0; ix < R2X_VTILE; ++ix) {
+            const float dx = r0.x - (fx0 + (float)ix);
+            float X0 = 0.f, Xy = 0.f, Xyy = 0.f, Xz = 0.f, Xyz = 0.f, Xzz = 0.f;
+#pragma unroll 1
+            for (int iy = 0; iy < R2X_VTILE; ++iy) {
+                const float dy = r0.y - (fy0 + (float)iy);
+                const float q0 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), (r1.w * dy) * dy);
+                const float lin = fmaf(r1.z, dx, r2.x * dy);
+                const float4 da = *reinterpret_cast<const float4*>(&s_dl[ix][iy][0]);
+                const float4 db = *reinterpret_cast<const float4*>(&s_dl[ix][iy][4]);
+                const float dlv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                float R0 = 0.f, Rz = 0.f, Rzz = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float dz = dz0 - (float)k;
+                    const float u = fmaf(r2.y, dz, lin);
+                    const float p = fmaf(dz, u, q0);
+                    const float G = ex2_approx(p);
+                    const float al = r0.w * G;
+                    const float t = (!(p > 0.0f) && !(al < 0.000001f)) ? dlv[k] * G : 0.f;
+                    R0 += t;
+                    const float tdz = t * dz;
+                    Rz += tdz;
+                    Rzz = fmaf(tdz, dz, Rzz);
+                }
+                X0 += R0; Xz += Rz; Xzz += Rzz;
+                Xy = fmaf(dy, R0, Xy);
+                Xyy = fmaf(dy * dy, R0, Xyy);
+                Xyz = fmaf(dy, Rz, Xyz);
+            }
+            S0 += X0; Sy += Xy; Sz += Xz; Syy += Xyy; Syz += Xyz; Szz += Xzz;
+            Sx = fmaf(dx, X0, Sx);
+            Sxx = fmaf(dx * dx, X0, Sxx);
+            Sxy = fmaf(dx, Xy, Sxy);
+            Sxz = fmaf(dx, Xz, Sxz);
+        }
+        inst_grad[3 * (size_t)s] = make_float4(S0, Sx, Sy, Sz);
+        inst_grad[3 * (size_t)s + 1] = make_float4(Sxx, Sxy, Sxz, Syy);
+        inst_grad[3 * (size_t)s + 2] = make_float4(Syz, Szz, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, per Gaussian
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
+    int P, const int* __restrict__ radii_x, const int* __restrict__ radii_y, const int* __restrict__ radii_z,
+    const float* __restrict__ scales, float scale_modifier, const float* __restrict__ rots,
+    const float* __restrict__ cov3D_precomp, VoxelGrid vg, VoxelGeom geom, const uint32_t* __restrict__ inst_pos,
+    const float4* __restrict__ inst_grad, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmean3D,
+    float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P) return;
+    const bool live = (radii_x[g] > 0) && (radii_y[g] > 0) && (radii_z[g] > 0);
+    float dop = 0.f, dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ds[3] = {0.f, 0.f, 0.f}, dr[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const uint32_t n = geom.tiles_touched[g];
+        const uint32_t start = geom.offsets[g] - n;
+        float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t s = inst_pos[start + k];
+            const float4 a = inst_grad[3 * (size_t)s];
+            const float4 b = inst_grad[3 * (size_t)s + 1];
+            const float4 c = inst_grad[3 * (size_t)s + 2];
+            S0 += a.x; Sx += a.y; Sy += a.z; Sz += a.w;
+            Sxx += b.x; Sxy += b.y; Sxz += b.z; Syy += b.w;
+            Syz += c.x; Szz += c.y;
+        }
+        const float rho = geom.rec[4 * (size_t)g].w;
+        const bool have_sr = (cov3D_precomp == nullptr);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        float c3[6];
+        if (have_sr) {
+            s0 = scales[3 * (size_t)g]; s1 = scales[3 * (size_t)g + 1]; s2 = scales[3 * (size_t)g + 2];
+            q = make_float4(rots[4 * (size_t)g], rots[4 * (size_t)g + 1], rots[4 * (size_t)g + 2], rots[4 * (size_t)g + 3]);
+            cov3d_from_scale_rot(s0, s1, s2, scale_modifier, q, c3);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c3[k] = cov3D_precomp[6 * (size_t)g + k];
+        }
+        const VoxCov vc = voxel_cov(c3, vg.ix, vg.iy, vg.iz);
+        float inv[6];
+        voxel_inverse(vc, inv);
+        // VOX/backward.cu:348-370 with the per-pair sums factored into moments
+        dop = S0;
+        dmean[0] = rho * (-inv[0] * Sx - inv[1] * Sy - inv[2] * Sz) * vg.dvx;   // note: x dVoxel, as the reference
+        dmean[1] = rho * (-inv[3] * Sy - inv[1] * Sx - inv[4] * Sz) * vg.dvy;
+        dmean[2] = rho * (-inv[5] * Sz - inv[2] * Sx - inv[4] * Sy) * vg.dvz;
+        const float ga = -0.5f * rho * Sxx, gb = -rho * Sxy, gc = -rho * Sxz, gd = -0.5f * rho * Syy, ge = -rho * Syz,
+                    gf = -0.5f * rho * Szz;
+        const float a = vc.a, b = vc.b, c = vc.c, d = vc.d, e = vc.e, f = vc.f;
+        const float denom = a * d * f + 2 * b * c * e - a * e * e - f * b * b - d * c * c;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0.f) {
+            const float n_da = d * f - e * e, n_db = 2 * c * e - 2 * f * b, n_dc = 2 * b * e - 2 * d * c;
+            const float n_dd = a * f - c * c, n_de = 2 * b * c - 2 * a * e, n_df = a * d - b * b;
+            const float ce_bf = c * e - b * f, be_cd = b * e - c * d, bc_ae = b * c - a * e;
+            float dh[6];
+            dh[0] = denom2inv * (-n_da*n_da*ga - ce_bf*n_da*gb - be_cd*n_da*gc + (f*denom-n_dd*n_da)*gd + (-e*denom-bc_ae*n_da)*ge + (d*denom-n_df*n_da)*gf);
+            dh[1] = denom2inv * (-n_da*n_db*ga + (-f*denom-ce_bf*n_db)*gb + (e*denom-be_cd*n_db)*gc - n_dd*n_db*gd + (c*denom-bc_ae*n_db)*ge + (-2*b*denom-n_df*n_db)*gf);
+            dh[2] = denom2inv * (-n_da*n_dc*ga + (e*denom-ce_bf*n_dc)*gb + (-d*denom-be_cd*n_dc)*gc + (-2*c*denom-n_dd*n_dc)*gd + (b*denom-bc_ae*n_dc)*ge - n_df*n_dc*gf);
+            dh[3] = denom2inv * ((f*denom-n_da*n_dd)*ga - ce_bf*n_dd*gb + (-c*denom-be_cd*n_dd)*gc - n_dd*n_dd*gd - bc_ae*n_dd*ge + (a*denom-n_df*n_dd)*gf);
+            dh[4] = denom2inv * ((-2*e*denom-n_da*n_de)*ga + (c*denom-ce_bf*n_de)*gb + (b*denom-be_cd*n_de)*gc - n_dd*n_de*gd + (-a*denom-bc_ae*n_de)*ge + -n_df*n_de*gf);
+            dh[5] = denom2inv * ((d*denom-n_da*n_df)*ga + (-b*denom-ce_bf*n_df)*gb - be_cd*n_df*gc + (a*denom-n_dd*n_df)*gd - bc_ae*n_df*ge - n_df*n_df*gf);
+            const float Mm[9] = {vg.ix, 0.f, 0.f, 0.f, vg.iy, 0.f, 0.f, 0.f, vg.iz};
+            dcov3d_from_dhat(Mm, dh, dcov);
+        }
+        if (have_sr) cov3d_backward(s0, s1, s2, scale_modifier, q, dcov, ds, dr);
+    }
+    dL_dopacity[g] = dop;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dL_dmean3D[3 * (size_t)g + k] = dmean[k]; dL_dscale[3 * (size_t)g + k] = ds[k]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)g + k] = dcov[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dL_drot[4 * (size_t)g + k] = dr[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+VoxelGrid make_voxel_grid(int nx, int ny, int nz, float sx, float sy, float sz, float cx, float cy, float cz) {
+    VoxelGrid v;
+    v.nx = nx; v.ny = ny; v.nz = nz;
+    v.sx = sx; v.sy = sy; v.sz = sz;
+    v.cx = cx; v.cy = cy; v.cz = cz;
+    v.gx = (nx + R2X_VTILE - 1) / R2X_VTILE;
+    v.gy = (ny + R2X_VTILE - 1) / R2X_VTILE;
+    v.gz = (nz + R2X_VTILE - 1) / R2X_VTILE;
+    // IEEE float32 divisions on the host == div.rn.f32 / rcp.rn.f32 on the device
+    volatile float dvx = sx / (float)nx, dvy = sy / (float)ny, dvz = sz / (float)nz;
+    v.dvx = dvx; v.dvy = dvy; v.dvz = dvz;
+    volatile float ix = 1.0f / dvx, iy = 1.0f / dvy, iz = 1.0f / dvz;
+    v.ix = ix; v.iy = iy; v.iz = iz;
+    return v;
+}
+
+int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const float* scales, float scale_modifier,
+                            const float* rots, const float* opac, const float* cov3D_precomp, const VoxelGrid& vg,
+                            int* radii_x, int* radii_y, int* radii_z, const VoxelGeom& geom) {
+    if (P <= 0) return 0;
+    auto al16 = [](const void* p) { return p && (((size_t)p) & 15) == 0; };
+    const int use_tma = al16(means) && al16(opac) && al16(scales) && al16(rots);
+    voxel_preprocess_kernel<<<(P + VPRE_THREADS - 1) / VPRE_THREADS, VPRE_THREADS, 0, st>>>(
+        P, means, scales, scale_modifier, rots, opac, cov3D_precomp, vg, use_tma, radii_x, radii_y, radii_z, geom);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_voxel_render(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
+                        const uint32_t* point_list, float* out_volume) {
+    const int tiles = vg.gx * vg.gy * vg.gz;
+    voxel_render_kernel<<<tiles, VR_THREADS, 0, st>>>(vg, ranges, point_list, geom.rec, out_volume);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
+                            const uint32_t* point_list, const float* dL_dvol, float4* inst_grad) {
+    const int tiles = vg.gx * vg.gy * vg.gz;
+    voxel_render_bwd_kernel<<<tiles, 256, 0, st>>>(vg, ranges, point_list, geom.rec, dL_dvol, inst_grad);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_voxel_gauss_bwd(cudaStream_t st, int P, const int* radii_x, const int* radii_y, const int* radii_z,
+                           const float* scales, float scale_modifier, const float* rots, const float* cov3D_precomp,
+                           const VoxelGrid& vg, const VoxelGeom& geom, const uint32_t* inst_pos,
+                           const float4* inst_grad, float* dL_dopacity, float* dL_dmean3D, float* dL_dcov3D,
+                           float* dL_dscale, float* dL_drot) {
+    if (P <= 0) return 0;
+    voxel_gauss_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii_x, radii_y, radii_z, scales, scale_modifier, rots,
+                                                             cov3D_precomp, vg, geom, inst_pos, inst_grad, dL_dopacity,
+                                                             dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace r2x

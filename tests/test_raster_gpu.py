@@ -1,0 +1,103 @@
+"""GPU parity: our sm_100a rasterizer (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): bit-exact radii / tiles_touched / tile rectangles / depth bits / the
+multiset of 64-bit sort keys; pixel intensities within 1e-5 relative (of the image scale -- a pair that
+sits exactly on the alpha = 1e-5 cut may flip and moves a pixel by 1e-5 absolute); gradients within
+1e-4 relative of the gradient scale (the reference's own float atomics are not order-stable)."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cone_init_small", "cone_trained_small", "parallel_trained_small", "cone_trained_ragged", "cone_trained_mid"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_oracle(name):
+    cloud, view = util.case(name)
+    ours = util.ours_raster_forward(cloud, view)
+    orc = util.oracle_raster_forward(cloud, view)
+    # --- bit-exact territory
+    assert ours["R"] == orc["R"]
+    np.testing.assert_array_equal(ours["radii"], orc["radii"])
+    np.testing.assert_array_equal(ours["tiles_touched"], orc["tiles_touched"])
+    vis = orc["radii"] > 0
+    np.testing.assert_array_equal(ours["depth"][vis].view(np.uint32), orc["depth"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["xy"][vis].view(np.uint32), orc["xy"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["point_offsets"], np.cumsum(orc["tiles_touched"]).astype(np.uint32))
+    assert util.key_multiset_equal(ours["keys"], orc["keys"])
+    # per-tile ranges identical; our per-tile lists hold the same Gaussians (ascending id instead of depth order)
+    np.testing.assert_array_equal(ours["ranges"], orc["ranges"])
+    for t in range(orc["ranges"].shape[0]):
+        a, b = orc["ranges"][t]
+        mine = ours["point_list"][a:b]
+        assert np.all(np.diff(mine.astype(np.int64)) > 0), "per-tile list must be strictly ascending in Gaussian id"
+        np.testing.assert_array_equal(mine, np.sort(orc["point_list"][a:b]))
+    # --- tolerance territory
+    np.testing.assert_allclose(ours["conic_opacity"][vis], orc["conic_opacity"][vis], rtol=0, atol=0)
+    np.testing.assert_array_equal(ours["mu"][vis].view(np.uint32), orc["mu"][vis].view(np.uint32))
+    scale = float(np.abs(orc["image"]).max())
+    err = np.abs(ours["image"].astype(np.float64) - orc["image"]).max()
+    assert err <= 1e-5 * scale + 1e-7, f"image error {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("name", ["cone_trained_small", "parallel_trained_small", "cone_trained_ragged"])
+def test_backward_matches_oracle(name):
+    cloud, view = util.case(name)
+    ours = util.ours_raster_forward(cloud, view, export=False)
+    orc = util.oracle_raster_forward(cloud, view)
+    rng = np.random.RandomState(7)
+    dL = rng.randn(view.image_height, view.image_width).astype(np.float32)
+    g = util.ours_raster_backward(cloud, view, ours, dL)
+    go = util.oracle_raster_backward(cloud, view, orc, dL)
+    for k in ["dL_dmean2D", "dL_dopacity", "dL_dmu", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]:
+        e = util.rel_err(g[k], go[k])
+        assert e < 2e-4, f"{k}: rel err {e}"
+
+
+def test_forward_is_deterministic():
+    cloud, view = util.case("cone_trained_mid")
+    a = util.ours_raster_forward(cloud, view, export=False)["image"]
+    b = util.ours_raster_forward(cloud, view, export=False)["image"]
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_backward_is_deterministic():
+    cloud, view = util.case("cone_trained_small")
+    dL = np.random.RandomState(3).randn(view.image_height, view.image_width).astype(np.float32)
+    f = util.ours_raster_forward(cloud, view, export=False)
+    g1 = util.ours_raster_backward(cloud, view, f, dL)
+    g2 = util.ours_raster_backward(cloud, view, f, dL)
+    for k in g1:
+        np.testing.assert_array_equal(g1[k].view(np.uint32), g2[k].view(np.uint32))
+
+
+def test_empty_and_culled_inputs():
+    import torch
+    from r2_gaussian_b200 import _C
+
+    cloud, view = util.case("cone_trained_small")
+    t = util.to_torch(cloud, view)
+    # P = 0: zeros, num_rendered 0 (reference SUB/rasterize_points.cu:70-72)
+    e3 = torch.zeros((0, 3), device="cuda"); e1 = torch.zeros((0, 1), device="cuda"); e4 = torch.zeros((0, 4), device="cuda")
+    R, color, radii, *_ = _C.rasterize_gaussians(e3, e1, e3, e4, 1.0, torch.Tensor([]), t["view"], t["proj"],
+                                                 view.tanfovx, view.tanfovy, view.image_height, view.image_width,
+                                                 t["campos"], False, view.mode, False)
+    assert R == 0 and radii.numel() == 0 and float(color.abs().max()) == 0.0
+    # everything behind the near plane: all radii 0, empty image
+    far = t["means"].clone(); far[:] = torch.tensor(view.campos, device="cuda")  # at the source => z_view = 0
+    R, color, radii, *_ = _C.rasterize_gaussians(far, t["dens"], t["scales"], t["rots"], 1.0, torch.Tensor([]),
+                                                 t["view"], t["proj"], view.tanfovx, view.tanfovy, view.image_height,
+                                                 view.image_width, t["campos"], False, view.mode, False)
+    assert R == 0 and int(radii.max()) == 0 and float(color.abs().max()) == 0.0
+
+
+def test_cpu_tensor_is_rejected():
+    import torch
+    from r2_gaussian_b200 import _C
+
+    with pytest.raises(RuntimeError):
+        _C.rasterize_gaussians(torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4), 1.0,
+                               torch.Tensor([]), torch.eye(4), torch.eye(4), 1.0, 1.0, 16, 16, torch.zeros(3), False, 1, False)

@@ -1,0 +1,203 @@
+"""Shared helpers for the parity tests: scene cases, running our C ABI, the oracle and (GPU box only)
+the compiled reference in oracle/_ref."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from r2_gaussian_b200 import scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libr2ref.so")
+
+
+def case(name: str):
+    """Named small scenes: returns (cloud, view)."""
+    kind, beam, P, n = {
+        "cone_init_small": ("init", "cone", 3000, 128),
+        "cone_trained_small": ("trained", "cone", 3000, 128),
+        "parallel_trained_small": ("trained", "parallel", 2000, 96),
+        "cone_trained_ragged": ("trained", "cone", 1500, 100),   # detector not a multiple of 16
+        "cone_trained_mid": ("trained", "cone", 20000, 256),
+        "cone_init_mid": ("init", "cone", 50000, 256),
+    }[name]
+    sc = scene.cone_beam_scanner(n, 64) if beam == "cone" else scene.parallel_beam_scanner(n, 64)
+    view = scene.make_view(sc, 0.37 + 0.1 * len(name))
+    cloud = scene.make_cloud(P, kind=kind, seed=len(name))
+    return cloud, view
+
+
+def to_torch(cloud, view, device="cuda", requires_grad=False):
+    import torch
+
+    t = dict(
+        means=torch.tensor(cloud.means, device=device), scales=torch.tensor(cloud.scales, device=device),
+        rots=torch.tensor(cloud.rotations, device=device), dens=torch.tensor(cloud.density, device=device),
+    )
+    if requires_grad:
+        for v in t.values():
+            v.requires_grad_(True)
+    if view is not None:
+        t["view"] = torch.tensor(view.viewmatrix, device=device)
+        t["proj"] = torch.tensor(view.projmatrix, device=device)
+        t["campos"] = torch.tensor(view.campos, device=device)
+    return t
+
+
+def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None):
+    import torch
+    from r2_gaussian_b200 import _C
+    from r2_gaussian_b200._lib import load, check
+
+    t = to_torch(cloud, view)
+    empty = torch.Tensor([])
+    scales, rots, cov = t["scales"], t["rots"], empty
+    if cov3D_precomp is not None:
+        scales, rots, cov = empty, empty, torch.tensor(cov3D_precomp, device="cuda")
+    R, color, radii, geom, binning, img = _C.rasterize_gaussians(
+        t["means"], t["dens"], scales, rots, 1.0, cov, t["view"], t["proj"], view.tanfovx, view.tanfovy,
+        view.image_height, view.image_width, t["campos"], False, view.mode, False)
+    out = dict(R=R, image=color[0].cpu().numpy(), radii=radii.cpu().numpy(), state=(geom, binning, img), t=t)
+    if export:
+        lib = load()
+        P, W, H = cloud.P, view.image_width, view.image_height
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        dev = "cuda"
+        xy = torch.empty((P, 2), device=dev); depth = torch.empty(P, device=dev)
+        co = torch.empty((P, 4), device=dev); mu = torch.empty(P, device=dev)
+        tt = torch.empty(P, dtype=torch.int32, device=dev); po = torch.empty(P, dtype=torch.int32, device=dev)
+        keys = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
+        pl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+        ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        rc = lib.r2x_raster_export(torch.cuda.current_stream().cuda_stream, P, W, H, R, geom.data_ptr(),
+                                   binning.data_ptr() if binning.numel() else None, img.data_ptr(), xy.data_ptr(),
+                                   depth.data_ptr(), co.data_ptr(), mu.data_ptr(), tt.data_ptr(), po.data_ptr(),
+                                   keys.data_ptr(), pl.data_ptr(), ranges.data_ptr())
+        check(rc, "r2x_raster_export")
+        torch.cuda.synchronize()
+        out.update(xy=xy.cpu().numpy(), depth=depth.cpu().numpy(), conic_opacity=co.cpu().numpy(), mu=mu.cpu().numpy(),
+                   tiles_touched=tt.cpu().numpy().astype(np.uint32), point_offsets=po.cpu().numpy().astype(np.uint32),
+                   keys=keys.cpu().numpy().astype(np.uint64)[:R], point_list=pl.cpu().numpy().astype(np.uint32)[:R],
+                   ranges=ranges.cpu().numpy().astype(np.uint32))
+    return out
+
+
+def ours_raster_backward(cloud, view, fwd, dL):
+    import torch
+    from r2_gaussian_b200 import _C
+
+    t = fwd["t"]
+    geom, binning, img = fwd["state"]
+    radii = torch.tensor(fwd["radii"], device="cuda")
+    g = _C.rasterize_gaussians_backward(
+        t["means"], radii, t["scales"], t["rots"], 1.0, torch.Tensor([]), t["view"], t["proj"], view.tanfovx,
+        view.tanfovy, torch.tensor(dL, device="cuda")[None], t["campos"], geom, fwd["R"], binning, img, view.mode, False)
+    names = ["dL_dmean2D", "dL_dopacity", "dL_dmu", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]
+    return {n: x.cpu().numpy() for n, x in zip(names, g)}
+
+
+def oracle_raster_forward(cloud, view, **kw):
+    from oracle import r2_oracle as orc
+
+    return orc.raster_forward(cloud.means, cloud.scales, cloud.rotations, cloud.density, view.viewmatrix,
+                              view.projmatrix, view.image_width, view.image_height, view.tanfovx, view.tanfovy,
+                              view.mode, **kw)
+
+
+def oracle_raster_backward(cloud, view, fwd, dL):
+    from oracle import r2_oracle as orc
+
+    return orc.raster_backward(fwd, cloud.means, cloud.scales, cloud.rotations, view.viewmatrix, view.projmatrix,
+                               view.image_width, view.image_height, view.tanfovx, view.tanfovy, view.mode, dL)
+
+
+# ---- voxelizer ------------------------------------------------------------------------------
+def ours_voxel_forward(cloud, nVoxel, sVoxel, center, export=True):
+    import torch
+    from r2_gaussian_b200 import _C
+    from r2_gaussian_b200._lib import load, check
+
+    t = to_torch(cloud, None)
+    R, vol, rx, ry, rz, geom, binning, img = _C.voxelize_gaussians(
+        t["means"], t["dens"], t["scales"], t["rots"], 1.0, torch.Tensor([]), nVoxel[0], nVoxel[1], nVoxel[2],
+        sVoxel[0], sVoxel[1], sVoxel[2], center[0], center[1], center[2], False, False)
+    out = dict(R=R, vol=vol.cpu().numpy(), radii_x=rx.cpu().numpy(), radii_y=ry.cpu().numpy(), radii_z=rz.cpu().numpy(),
+               state=(geom, binning, img), t=t, radii_t=(rx, ry, rz))
+    if export:
+        lib = load()
+        P = cloud.P
+        nx, ny, nz = nVoxel
+        T = ((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8)
+        dev = "cuda"
+        xyz = torch.empty((P, 3), device=dev); depth = torch.empty(P, device=dev); co = torch.empty((P, 7), device=dev)
+        tt = torch.empty(P, dtype=torch.int32, device=dev); po = torch.empty(P, dtype=torch.int32, device=dev)
+        keys = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
+        pl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+        ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        rc = lib.r2x_voxel_export(torch.cuda.current_stream().cuda_stream, P, nx, ny, nz, R, geom.data_ptr(),
+                                  binning.data_ptr() if binning.numel() else None, img.data_ptr(), xyz.data_ptr(),
+                                  depth.data_ptr(), co.data_ptr(), tt.data_ptr(), po.data_ptr(), keys.data_ptr(),
+                                  pl.data_ptr(), ranges.data_ptr())
+        check(rc, "r2x_voxel_export")
+        torch.cuda.synchronize()
+        out.update(xyz_vol=xyz.cpu().numpy(), depth=depth.cpu().numpy(), conic_opacity=co.cpu().numpy(),
+                   tiles_touched=tt.cpu().numpy().astype(np.uint32), keys=keys.cpu().numpy().astype(np.uint64)[:R],
+                   point_list=pl.cpu().numpy().astype(np.uint32)[:R], ranges=ranges.cpu().numpy().astype(np.uint32))
+    return out
+
+
+def ours_voxel_backward(cloud, nVoxel, sVoxel, center, fwd, dL):
+    import torch
+    from r2_gaussian_b200 import _C
+
+    t = fwd["t"]
+    geom, binning, img = fwd["state"]
+    rx, ry, rz = fwd["radii_t"]
+    g = _C.voxelize_gaussians_backward(
+        t["means"], rx, ry, rz, t["scales"], t["rots"], 1.0, torch.Tensor([]), torch.tensor(dL, device="cuda"), geom,
+        fwd["R"], binning, img, nVoxel[0], nVoxel[1], nVoxel[2], sVoxel[0], sVoxel[1], sVoxel[2], center[0], center[1],
+        center[2], False)
+    names = ["dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]
+    return {n: x.cpu().numpy() for n, x in zip(names, g)}
+
+
+def oracle_voxel_forward(cloud, nVoxel, sVoxel, center, **kw):
+    from oracle import r2_oracle as orc
+
+    return orc.voxel_forward(cloud.means, cloud.scales, cloud.rotations, cloud.density, nVoxel, sVoxel, center, **kw)
+
+
+def oracle_voxel_backward(cloud, nVoxel, sVoxel, fwd, dL):
+    from oracle import r2_oracle as orc
+
+    return orc.voxel_backward(fwd, cloud.scales, cloud.rotations, nVoxel, sVoxel, dL)
+
+
+# ---- comparison helpers ---------------------------------------------------------------------
+def key_multiset_equal(keys_a, keys_b):
+    return np.array_equal(np.sort(np.asarray(keys_a, dtype=np.uint64)), np.sort(np.asarray(keys_b, dtype=np.uint64)))
+
+
+def rel_err(a, b, floor=None):
+    """max |a-b| / max(|b|, floor) -- floor defaults to 1e-3 * max|b| (relative to the signal scale)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if floor is None:
+        floor = 1e-3 * (np.abs(b).max() if b.size else 1.0) + 1e-30
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max()) if a.size else 0.0
+
+
+# ---- the compiled reference (GPU box) ---------------------------------------------------------
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_LIB):
+            return None
+        _ref = C.CDLL(REF_LIB)
+        _ref.ref_raster_forward.restype = C.c_int
+        _ref.ref_voxel_forward.restype = C.c_int
+    return _ref
