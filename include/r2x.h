@@ -98,6 +98,14 @@ int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const fl
                         float* dL_dmean3D, float* dL_dcov3D, float* dL_dscale, float* dL_drot, int mode,
                         int debug);
 
+/* Stage entry points for measurement (bench.py roofline, ncu): re-run ONLY the per-tile accumulation
+ * kernel (the reference's renderCUDA, RAS/forward.cu:294-395 / VOX/forward.cu:183-315) on the state a
+ * previous forward left in the three buffers.  `R` = the count the binning buffer was carved for. */
+int r2x_raster_render_only(void* stream, int P, int W, int H, long long R, const void* geom_buf,
+                           const void* binning_buf, const void* image_buf, float* out_color);
+int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long R, const void* geom_buf,
+                          const void* binning_buf, const void* image_buf, float* out_volume);
+
 int r2x_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, unsigned char* present);
 

@@ -73,20 +73,27 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 static void cov3d_from_scale_rot(const float* scale, float mod, const float* q, float* cov) {
     float sx = mod * scale[0], sy = mod * scale[1], sz = mod * scale[2];
     float r = q[0], x = q[1], y = q[2], z = q[3];
-    float yy = y * y, zz = z * z;
-    float xy = x * y, rz = r * z, xz = x * z, ry = r * y, yz = y * z, rx = r * x;
+    /* SASS-level contraction (ptxas fuses further than the PTX shows): the products r*x, r*z, x*z and
+     * y*y, z*z are rounded; every other product of the rotation entries rides inside an FMA. */
+    float yy = y * y, zz = z * z, xz = x * z, rx = r * x, rz = r * z;
     float yy_zz = yy + zz;
     float xx_zz = fmaf(x, x, zz);
     float xx_yy = fmaf(x, x, yy);
+    float ry_xz = fmaf(r, y, xz);    /* x*z + r*y */
+    float xz_ry = fmaf(-r, y, xz);   /* x*z - r*y */
+    float yz_rx_m = fmaf(y, z, -rx); /* y*z - r*x */
+    float yz_rx_p = fmaf(y, z, rx);  /* y*z + r*x */
+    float xy_rz_m = fmaf(x, y, -rz); /* x*y - r*z */
+    float xy_rz_p = fmaf(x, y, rz);  /* x*y + r*z */
     /* textual rows of R in the reference; glm columns */
     float R00 = 1.0f - (yy_zz + yy_zz);
-    float R01 = (xy - rz) + (xy - rz);
-    float R02 = (ry + xz) + (ry + xz);
-    float R10 = (xy + rz) + (xy + rz);
+    float R01 = xy_rz_m + xy_rz_m;
+    float R02 = ry_xz + ry_xz;
+    float R10 = xy_rz_p + xy_rz_p;
     float R11 = 1.0f - (xx_zz + xx_zz);
-    float R12 = (yz - rx) + (yz - rx);
-    float R20 = (xz - ry) + (xz - ry);
-    float R21 = (rx + yz) + (rx + yz);
+    float R12 = yz_rx_m + yz_rx_m;
+    float R20 = xz_ry + xz_ry;
+    float R21 = yz_rx_p + yz_rx_p;
     float R22 = 1.0f - (xx_yy + xx_yy);
     /* M = S * R (glm):  M[c][r] = s_r * Rcol[c][r]; Rcol[0]=(R00,R01,R02) ... */
     float M00 = sx * R00, M01 = sy * R01, M02 = sz * R02;
@@ -164,9 +171,9 @@ static void raster_cov_from_M(const float* Mm, const float* c3, float* hat) {
 static inline float det3_ref(float a, float b, float c, float d, float e, float f, float ad) {
     float t = ad * f;
     t = fmaf((b + b) * c, e, t);
-    t = t - e * (a * e);
-    t = t - b * (b * f);
-    t = t - c * (c * d);
+    t = fmaf(-e, a * e, t);
+    t = fmaf(-b, b * f, t);
+    t = fmaf(-c, c * d, t);
     return t;
 }
 
@@ -215,13 +222,13 @@ long long orc_raster_preprocess(int P, const float* means, const float* scales, 
         raster_cov_from_M(Mm, c3, hat);
         float a = hat[0], b = hat[1], c = hat[2], d = hat[3], e = hat[4], f = hat[5];
         float ad = a * d;
-        float det = ad - b * b; /* diamond, RAS/forward.cu:147 == det, :261 */
+        float det = fmaf(-b, b, ad); /* diamond, RAS/forward.cu:147 == det, :261 */
         float circ = det3_ref(a, b, c, d, e, f, ad);
         if (det == 0.0f) continue;
         float det_inv = 1.0f / det;
         float conx = d * det_inv, cony = det_inv * (-b), conz = a * det_inv;
         float mid = (a + d) * 0.5f;
-        float disc = sqrtf(fmaxf(mid * mid - det, 0.1f));
+        float disc = sqrtf(fmaxf(fmaf(mid, mid, -det), 0.1f));
         float lam = fmaxf(mid + disc, mid - disc);
         float my_radius = ceilf(sqrtf(lam) * 3.0f);
         /* ndc2Pix in float64, RAS/auxiliary.h:45-48 */
@@ -657,17 +664,17 @@ long long orc_voxel_preprocess(int P, const float* means, const float* scales, f
         float ad = a * d, ae = a * e, bf = b * f, cd = c * d;
         float det = ad * f;
         det = fmaf((b + b) * c, e, det);
-        det = det - e * ae;
-        det = det - b * bf;
-        det = det - c * cd;
+        det = fmaf(-e, ae, det);
+        det = fmaf(-b, bf, det);
+        det = fmaf(-c, cd, det);
         if (det == 0.0f) continue;
         float di = 1.0f / det;
-        float inv_a = (d * f - e * e) * di;
-        float inv_b = (c * e - bf) * di;
-        float inv_c = (b * e - cd) * di;
-        float inv_d = (a * f - c * c) * di;
-        float inv_e = (b * c - ae) * di;
-        float inv_f = (ad - b * b) * di;
+        float inv_a = fmaf(d, f, -(e * e)) * di;
+        float inv_b = fmaf(c, e, -bf) * di;
+        float inv_c = fmaf(b, e, -cd) * di;
+        float inv_d = fmaf(a, f, -(c * c)) * di;
+        float inv_e = fmaf(b, c, -ae) * di;
+        float inv_f = fmaf(-b, b, ad) * di;
         const float* s = scales + 3 * i; /* read unconditionally, VOX/forward.cu:137 */
         float ms3 = fmaxf(fmaxf(s[0], s[1]), s[2]) * 3.0f;
         float rx = ceilf(ms3 / dvx), ry = ceilf(ms3 / dvy), rz = ceilf(ms3 / dvz);

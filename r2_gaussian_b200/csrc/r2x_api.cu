@@ -337,6 +337,27 @@ int r2x_raster_forward_async(void* stream, int P, int W, int H, const float* mea
                                status_dev, 0, nullptr);
 }
 
+int r2x_raster_render_only(void* stream, int P, int W, int H, long long R, const void* geom_buf,
+                           const void* binning_buf, const void* image_buf, float* out_color) {
+    if (P <= 0 || R < 0 || !geom_buf || !image_buf || !out_color || (R > 0 && !binning_buf))
+        return fail_msg(R2X_ERR_INVALID, "r2x_raster_render_only: bad args");
+    RasterState s = carve_raster(geom_buf, P, W, H);
+    BinningView bv = binning_view((void*)binning_buf, R);
+    return launch_raster_render((cudaStream_t)stream, W, H, s.geom, (const uint2*)al((size_t)image_buf), bv.point_list,
+                                out_color);
+}
+
+int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long R, const void* geom_buf,
+                          const void* binning_buf, const void* image_buf, float* out_volume) {
+    if (P <= 0 || R < 0 || !geom_buf || !image_buf || !out_volume || (R > 0 && !binning_buf))
+        return fail_msg(R2X_ERR_INVALID, "r2x_voxel_render_only: bad args");
+    const VoxelGrid vg = make_voxel_grid(nx, ny, nz, 1.f, 1.f, 1.f, 0.f, 0.f, 0.f);  // render needs the tile grid only
+    VoxelState s = carve_voxel(geom_buf, P);
+    BinningView bv = binning_view((void*)binning_buf, R);
+    return launch_voxel_render((cudaStream_t)stream, vg, s.geom, (const uint2*)al((size_t)image_buf), bv.point_list,
+                               out_volume);
+}
+
 int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const float* means3D, const float* scales,
                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
@@ -359,7 +380,7 @@ int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const fl
     if (R > 0) R2X_TRY(launch_raster_render_bwd(st, W, H, s.geom, ranges, bv.point_list, dL_dpix, inst_grad));
     R2X_TRY(debug_sync(st, debug, "raster render backward"));
     R2X_TRY(launch_raster_gauss_bwd(st, P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
-                                    projmatrix, W, H, tan_fovx, tan_fovy, mode, s.geom, bv.inst_pos, inst_grad,
+                                    projmatrix, W, H, tan_fovx, tan_fovy, mode, s.geom, R, bv.inst_pos, inst_grad,
                                     dL_dmean2D, dL_dopacity, dL_dmu, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot));
     R2X_TRY(debug_sync(st, debug, "raster per-Gaussian backward"));
     return 0;
@@ -438,7 +459,7 @@ int r2x_voxel_backward(void* stream, int P, long long R, int nx, int ny, int nz,
     if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, dL_dvol, inst_grad));
     R2X_TRY(debug_sync(st, debug, "voxel render backward"));
     R2X_TRY(launch_voxel_gauss_bwd(st, P, radii_x, radii_y, radii_z, scales, scale_modifier, rotations, cov3D_precomp, vg,
-                                   s.geom, bv.inst_pos, inst_grad, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dscale,
+                                   s.geom, R, bv.inst_pos, inst_grad, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dscale,
                                    dL_drot));
     R2X_TRY(debug_sync(st, debug, "voxel per-Gaussian backward"));
     return 0;

@@ -45,13 +45,15 @@ __device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, f
 __device__ __forceinline__ void cov3d_from_scale_rot(float s0, float s1, float s2, float mod, float4 q, float* cov) {
     const float sx = fmul(mod, s0), sy = fmul(mod, s1), sz = fmul(mod, s2);
     const float r = q.x, x = q.y, y = q.z, z = q.w;
-    const float yy = fmul(y, y), zz = fmul(z, z);
-    const float xy = fmul(x, y), rz = fmul(r, z), xz = fmul(x, z), ry = fmul(r, y), yz = fmul(y, z), rx = fmul(r, x);
+    // (SASS-level contraction of the reference build: r*x, r*z, x*z, y*y, z*z are rounded products,
+    //  every other product rides inside an FMA)
+    const float yy = fmul(y, y), zz = fmul(z, z), xz = fmul(x, z), rx = fmul(r, x), rz = fmul(r, z);
     const float yy_zz = fadd(yy, zz);
     const float xx_zz = ffma(x, x, zz);
     const float xx_yy = ffma(x, x, yy);
-    const float a01 = fsub(xy, rz), a02 = fadd(ry, xz), a10 = fadd(xy, rz);
-    const float a12 = fsub(yz, rx), a20 = fsub(xz, ry), a21 = fadd(rx, yz);
+    const float a02 = ffma(r, y, xz), a20 = ffma(-r, y, xz);
+    const float a12 = ffma(y, z, -rx), a21 = ffma(y, z, rx);
+    const float a01 = ffma(x, y, -rz), a10 = ffma(x, y, rz);
     const float R00 = fsub(1.0f, fadd(yy_zz, yy_zz));
     const float R01 = fadd(a01, a01), R02 = fadd(a02, a02), R10 = fadd(a10, a10);
     const float R11 = fsub(1.0f, fadd(xx_zz, xx_zz));

@@ -25,8 +25,8 @@ int launch_raster_render_bwd(cudaStream_t st, int W, int H, const RasterGeom& ge
 int launch_raster_gauss_bwd(cudaStream_t st, int P, const float* means, const int* radii, const float* scales,
                             float scale_modifier, const float* rots, const float* cov3D_precomp, const float* view,
                             const float* proj, int W, int H, float tan_fovx, float tan_fovy, int mode,
-                            const RasterGeom& geom, const uint32_t* inst_pos, const float4* inst_grad,
-                            float* dL_dmean2D, float* dL_dopacity, float* dL_dmu, float* dL_dmean3D,
+                            const RasterGeom& geom, long long capacity, const uint32_t* inst_pos,
+                            const float4* inst_grad, float* dL_dmean2D, float* dL_dopacity, float* dL_dmu, float* dL_dmean3D,
                             float* dL_dcov3D, float* dL_dscale, float* dL_drot);
 int launch_mark_visible(cudaStream_t st, int P, const float* means, const float* view, unsigned char* present);
 

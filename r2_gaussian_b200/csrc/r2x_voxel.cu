@@ -35,9 +35,9 @@ __device__ __forceinline__ VoxCov voxel_cov(const float* c3, float ix, float iy,
     const float ad = fmul(v.a, v.d), ae = fmul(v.a, v.e), bf = fmul(v.b, v.f), cd = fmul(v.c, v.d);
     float det = fmul(ad, v.f);
     det = ffma(fmul(fadd(v.b, v.b), v.c), v.e, det);
-    det = fsub(det, fmul(v.e, ae));
-    det = fsub(det, fmul(v.b, bf));
-    det = fsub(det, fmul(v.c, cd));
+    det = ffma(-v.e, ae, det);
+    det = ffma(-v.b, bf, det);
+    det = ffma(-v.c, cd, det);
     v.det = det;
     return v;
 }
@@ -45,12 +45,12 @@ __device__ __forceinline__ VoxCov voxel_cov(const float* c3, float ix, float iy,
 __device__ __forceinline__ void voxel_inverse(const VoxCov& v, float* inv) {
     const float di = frcp(v.det);
     const float ad = fmul(v.a, v.d), ae = fmul(v.a, v.e), bf = fmul(v.b, v.f), cd = fmul(v.c, v.d);
-    inv[0] = fmul(fsub(fmul(v.d, v.f), fmul(v.e, v.e)), di);
-    inv[1] = fmul(fsub(fmul(v.c, v.e), bf), di);
-    inv[2] = fmul(fsub(fmul(v.b, v.e), cd), di);
-    inv[3] = fmul(fsub(fmul(v.a, v.f), fmul(v.c, v.c)), di);
-    inv[4] = fmul(fsub(fmul(v.b, v.c), ae), di);
-    inv[5] = fmul(fsub(ad, fmul(v.b, v.b)), di);
+    inv[0] = fmul(ffma(v.d, v.f, -fmul(v.e, v.e)), di);
+    inv[1] = fmul(ffma(v.c, v.e, -bf), di);
+    inv[2] = fmul(ffma(v.b, v.e, -cd), di);
+    inv[3] = fmul(ffma(v.a, v.f, -fmul(v.c, v.c)), di);
+    inv[4] = fmul(ffma(v.b, v.c, -ae), di);
+    inv[5] = fmul(ffma(-v.b, v.b, ad), di);
 }
 
 constexpr int VPRE_THREADS = 256;
@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
 __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
     int P, const int* __restrict__ radii_x, const int* __restrict__ radii_y, const int* __restrict__ radii_z,
     const float* __restrict__ scales, float scale_modifier, const float* __restrict__ rots,
-    const float* __restrict__ cov3D_precomp, VoxelGrid vg, VoxelGeom geom, const uint32_t* __restrict__ inst_pos,
+    const float* __restrict__ cov3D_precomp, VoxelGrid vg, VoxelGeom geom, long long capacity,
+    const uint32_t* __restrict__ inst_pos,
     const float4* __restrict__ inst_grad, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmean3D,
     float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
         const uint32_t start = geom.offsets[g] - n;
         float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
         for (uint32_t k = 0; k < n; ++k) {
+            if ((long long)start + k >= capacity) break;
             const uint32_t s = inst_pos[start + k];
             const float4 a = inst_grad[3 * (size_t)s];
             const float4 b = inst_grad[3 * (size_t)s + 1];
@@ -454,12 +456,12 @@ int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeo
 
 int launch_voxel_gauss_bwd(cudaStream_t st, int P, const int* radii_x, const int* radii_y, const int* radii_z,
                            const float* scales, float scale_modifier, const float* rots, const float* cov3D_precomp,
-                           const VoxelGrid& vg, const VoxelGeom& geom, const uint32_t* inst_pos,
+                           const VoxelGrid& vg, const VoxelGeom& geom, long long capacity, const uint32_t* inst_pos,
                            const float4* inst_grad, float* dL_dopacity, float* dL_dmean3D, float* dL_dcov3D,
                            float* dL_dscale, float* dL_drot) {
     if (P <= 0) return 0;
     voxel_gauss_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii_x, radii_y, radii_z, scales, scale_modifier, rots,
-                                                             cov3D_precomp, vg, geom, inst_pos, inst_grad, dL_dopacity,
+                                                             cov3D_precomp, vg, geom, capacity, inst_pos, inst_grad, dL_dopacity,
                                                              dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;

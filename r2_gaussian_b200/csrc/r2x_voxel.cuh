@@ -31,7 +31,7 @@ int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeo
                             const uint32_t* point_list, const float* dL_dvol, float4* inst_grad);
 int launch_voxel_gauss_bwd(cudaStream_t st, int P, const int* radii_x, const int* radii_y, const int* radii_z,
                            const float* scales, float scale_modifier, const float* rots, const float* cov3D_precomp,
-                           const VoxelGrid& vg, const VoxelGeom& geom, const uint32_t* inst_pos,
+                           const VoxelGrid& vg, const VoxelGeom& geom, long long capacity, const uint32_t* inst_pos,
                            const float4* inst_grad, float* dL_dopacity, float* dL_dmean3D, float* dL_dcov3D,
                            float* dL_dscale, float* dL_drot);
 

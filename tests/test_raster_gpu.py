@@ -52,9 +52,7 @@ def test_backward_matches_oracle(name):
     dL = rng.randn(view.image_height, view.image_width).astype(np.float32)
     g = util.ours_raster_backward(cloud, view, ours, dL)
     go = util.oracle_raster_backward(cloud, view, orc, dL)
-    for k in ["dL_dmean2D", "dL_dopacity", "dL_dmu", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]:
-        e = util.rel_err(g[k], go[k])
-        assert e < 2e-4, f"{k}: rel err {e}"
+    util.assert_grads_close(g, go, ["dL_dmean2D", "dL_dopacity", "dL_dmu", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"])
 
 
 def test_forward_is_deterministic():

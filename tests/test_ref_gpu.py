@@ -124,8 +124,7 @@ def test_oracle_pinned_to_reference_raster(name):
     scale = float(np.abs(ref["image"]).max())
     assert np.abs(ref["image"].astype(np.float64) - orc["image"]).max() <= 1e-5 * scale + 1e-7
     go = util.oracle_raster_backward(cloud, view, orc, dL)
-    for k, v in ref["grads"].items():
-        assert util.rel_err(v, go[k]) < 5e-4, k
+    util.assert_grads_close(go, ref["grads"], list(ref["grads"]), rtol=5e-4, atol_rel=5e-5, label="oracle vs ref ")
 
 
 @pytest.mark.parametrize("name", ["cone_trained_small", "cone_trained_mid"])
@@ -142,8 +141,7 @@ def test_ours_against_reference_raster(name):
     scale = float(np.abs(ref["image"]).max())
     assert np.abs(ours["image"].astype(np.float64) - ref["image"]).max() <= 1e-5 * scale + 1e-7
     g = util.ours_raster_backward(cloud, view, ours, dL)
-    for k, v in ref["grads"].items():
-        assert util.rel_err(g[k], v) < 5e-4, k
+    util.assert_grads_close(g, ref["grads"], list(ref["grads"]), rtol=5e-4, atol_rel=5e-5, label="ours vs ref ")
 
 
 @pytest.mark.parametrize("grid", [((32, 32, 32), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0)),
@@ -169,6 +167,5 @@ def test_oracle_and_ours_against_reference_voxel(grid):
     np.testing.assert_array_equal(orc["conic_opacity"][vis].view(np.uint32), ref["conic_opacity"][vis].view(np.uint32))
     go = util.oracle_voxel_backward(cloud, nV, sV, orc, dL)
     g = util.ours_voxel_backward(cloud, nV, sV, ctr, ours, dL)
-    for k, v in ref["grads"].items():
-        assert util.rel_err(go[k], v) < 5e-4, "oracle " + k
-        assert util.rel_err(g[k], v) < 5e-4, "ours " + k
+    util.assert_grads_close(go, ref["grads"], list(ref["grads"]), rtol=5e-4, atol_rel=5e-5, label="oracle vs ref ")
+    util.assert_grads_close(g, ref["grads"], list(ref["grads"]), rtol=5e-4, atol_rel=5e-5, label="ours vs ref ")

@@ -48,9 +48,7 @@ def test_backward_matches_oracle(name):
     dL = np.random.RandomState(11).randn(*nV).astype(np.float32)
     g = util.ours_voxel_backward(cloud, nV, sV, ctr, ours, dL)
     go = util.oracle_voxel_backward(cloud, nV, sV, orc, dL)
-    for k in ["dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]:
-        e = util.rel_err(g[k], go[k])
-        assert e < 2e-4, f"{k}: rel err {e}"
+    util.assert_grads_close(g, go, ["dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"])
 
 
 def test_deterministic():

@@ -188,6 +188,33 @@ def rel_err(a, b, floor=None):
     return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max()) if a.size else 0.0
 
 
+def grad_mismatch(a, b, rtol=2e-4, atol_rel=2e-5, scale=None):
+    """Worst violation of |a-b| <= rtol*|b| + atol_rel*scale (scale defaults to max|b|); <= 1 passes.
+
+    Gradients are sums of thousands of signed float32 terms: the achievable agreement between two
+    summation orders (the reference's float atomics are not even run-to-run stable) is relative to the
+    magnitude of the terms, not of the (possibly cancelling) sum, hence the absolute part tied to the
+    array's scale."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    if scale is None:
+        scale = float(np.abs(b).max())
+    tol = rtol * np.abs(b) + atol_rel * scale + 1e-30
+    return float((np.abs(a - b) / tol).max())
+
+
+def assert_grads_close(got: dict, want: dict, keys, rtol=2e-4, atol_rel=2e-5, label=""):
+    for k in keys:
+        scale = None
+        if k == "dL_drot":
+            # for isotropic Gaussians the rotation gradient is pure cancellation noise: tie its scale
+            # to the scale gradient (same chain, dL/dM times a parameter of order one)
+            scale = max(float(np.abs(want[k]).max()), float(np.abs(want["dL_dscale"]).max()))
+        m = grad_mismatch(got[k], want[k], rtol, atol_rel, scale)
+        assert m <= 1.0, f"{label}{k}: mismatch {m:.3g} x tolerance"
+
+
 # ---- the compiled reference (GPU box) ---------------------------------------------------------
 _ref = None
 
