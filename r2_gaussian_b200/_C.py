@@ -52,23 +52,50 @@ def _require_cuda(t: torch.Tensor, name: str):
         )
 
 
-class _BinningAlloc:
-    """Allocator handed to the synchronous forward for the R-dependent binning buffer."""
+class _Workspace:
+    """Per-(device, kind, size) instance-capacity hints so that the binning buffer can be provisioned
+    BEFORE the forward runs: the whole pipeline is then enqueued without a host round trip in the middle,
+    and the one synchronisation the reference API needs anyway (num_rendered is a Python int) happens at
+    the end.  If a call needs more instances than provisioned it is simply re-run with a larger buffer.
+    Capacities are rounded to a coarse grid so that torch's caching allocator sees repeating sizes."""
 
-    def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = ALLOC_FN(self._alloc)
+    hints: dict = {}
+    cap_of_bytes: dict = {}   # binning buffer size in bytes -> instance capacity it was carved for
 
-    def _alloc(self, nbytes, _user):
-        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.tensor.data_ptr()
+    @staticmethod
+    def _round(n: int) -> int:
+        step = 1 << max(12, int(n).bit_length() - 3)   # ~12.5 % granularity
+        return (int(n) + step - 1) // step * step
+
+    @classmethod
+    def capacity(cls, key, P: int, per_gaussian: int) -> int:
+        return cls.hints.get(key) or cls._round(max(per_gaussian * P, 1 << 14))
+
+    @classmethod
+    def update(cls, key, R: int):
+        want = cls._round(int(R * 1.2) + 1024)
+        cur = cls.hints.get(key, 0)
+        # grow immediately, shrink slowly (keeps sizes stable while the cloud changes during training)
+        cls.hints[key] = want if want > cur or want < cur // 2 else cur
+
+
+def _carved_capacity(binning: torch.Tensor, R: int) -> int:
+    """Instance count the binning buffer was carved for (what the backward must carve with)."""
+    return _Workspace.cap_of_bytes.get(int(binning.numel()), int(R)) if binning is not None else int(R)
+
+
+def _status_pair(dev):
+    st = torch.empty(2, dtype=torch.int32, device=dev)
+    return st
 
 
 def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                         projmatrix, tan_fovx, tan_fovy, image_height, image_width, campos, prefiltered, mode,
                         debug):
-    """-> (num_rendered, out_color[1,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)."""
+    """-> (num_rendered, out_color[1,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer).
+
+    The binning buffer is provisioned for a capacity >= num_rendered (see _Workspace); the backward
+    recovers that capacity from the buffer's size."""
     _require_cuda(means3D, "means3D")
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -79,20 +106,54 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
         means3D = _f32(means3D, dev); opacity = _f32(opacity, dev)
         scales = _f32(scales, dev); rotations = _f32(rotations, dev); cov3D_precomp = _f32(cov3D_precomp, dev)
         viewmatrix = _f32(viewmatrix, dev); projmatrix = _f32(projmatrix, dev); campos = _f32(campos, dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
         out_color = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom = torch.empty(lib.r2x_raster_geom_bytes(P), dtype=torch.uint8, device=dev)
-        img = torch.empty(lib.r2x_raster_image_bytes(W, H), dtype=torch.uint8, device=dev)
-        alloc = _BinningAlloc(dev)
-        nr = C.c_int(0)
-        rc = lib.r2x_raster_forward(
-            torch.cuda.current_stream(dev).cuda_stream, P, W, H, _ptr(means3D), _ptr(opacity), _ptr(scales),
-            float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix),
-            _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)), int(mode),
-            out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(), alloc.cb, None, int(bool(debug)),
-            C.byref(nr))
-        check(rc, "r2x_raster_forward")
-    return nr.value, out_color, radii, geom, alloc.tensor, img
+        geom = torch.empty(lib.r2x_raster_geom_bytes(P), **u8)
+        img = torch.empty(lib.r2x_raster_image_bytes(W, H), **u8)
+        status = _status_pair(dev)
+        key = ("raster", dev.index, P, W, H)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if debug or P == 0:
+            alloc = _BinningAlloc(dev)
+            nr = C.c_int(0)
+            rc = lib.r2x_raster_forward(
+                stream, P, W, H, _ptr(means3D), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                int(bool(prefiltered)), int(mode), out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(),
+                alloc.cb, None, int(bool(debug)), C.byref(nr))
+            check(rc, "r2x_raster_forward")
+            return nr.value, out_color, radii, geom, alloc.tensor, img
+        cap = _Workspace.capacity(key, P, 12)
+        while True:
+            nbytes = lib.r2x_binning_bytes(cap)
+            _Workspace.cap_of_bytes[int(nbytes)] = cap
+            binning = torch.empty(nbytes, **u8)
+            rc = lib.r2x_raster_forward_async(
+                stream, P, W, H, _ptr(means3D), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                int(bool(prefiltered)), int(mode), out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(),
+                binning.data_ptr(), cap, status.data_ptr())
+            check(rc, "r2x_raster_forward_async")
+            R, overflow = status.tolist()      # the one host synchronisation of the call
+            _Workspace.update(key, R)
+            if not overflow:
+                break
+            cap = _Workspace.capacity(key, P, 12)
+    return R, out_color, radii, geom, binning, img
+
+
+class _BinningAlloc:
+    """Allocator handed to the synchronous C entry point for the R-dependent binning buffer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, nbytes, _user):
+        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.tensor.data_ptr()
 
 
 def rasterize_gaussians_backward(means3D, radii, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
@@ -113,6 +174,7 @@ def rasterize_gaussians_backward(means3D, radii, scales, rotations, scale_modifi
         g_mean2D = torch.empty((P, 3), **opts); g_op = torch.empty((P, 1), **opts); g_mu = torch.empty((P, 1), **opts)
         g_mean3D = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
         g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        R = _carved_capacity(binningBuffer, R)
         scratch = torch.empty(lib.r2x_raster_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
         rc = lib.r2x_raster_backward(
             torch.cuda.current_stream(dev).cuda_stream, P, int(R), W, H, _ptr(means3D), _ptr(scales),
@@ -152,21 +214,42 @@ def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3
     with torch.cuda.device(dev):
         means3D = _f32(means3D, dev); opacity = _f32(opacity, dev)
         scales = _f32(scales, dev); rotations = _f32(rotations, dev); cov3D_precomp = _f32(cov3D_precomp, dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
         vol = torch.empty((nx, ny, nz), dtype=torch.float32, device=dev)
         rx = torch.empty((P,), dtype=torch.int32, device=dev)
         ry = torch.empty_like(rx); rz = torch.empty_like(rx)
-        geom = torch.empty(lib.r2x_voxel_geom_bytes(P), dtype=torch.uint8, device=dev)
-        img = torch.empty(lib.r2x_voxel_image_bytes(nx, ny, nz), dtype=torch.uint8, device=dev)
-        alloc = _BinningAlloc(dev)
-        nr = C.c_int(0)
-        rc = lib.r2x_voxel_forward(
-            torch.cuda.current_stream(dev).cuda_stream, P, nx, ny, nz, float(sVoxel_x), float(sVoxel_y),
-            float(sVoxel_z), float(center_x), float(center_y), float(center_z), _ptr(means3D), _ptr(opacity),
-            _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), int(bool(prefiltered)),
-            vol.data_ptr(), _ptr(rx), _ptr(ry), _ptr(rz), geom.data_ptr(), img.data_ptr(), alloc.cb, None,
-            int(bool(debug)), C.byref(nr))
-        check(rc, "r2x_voxel_forward")
-    return nr.value, vol, rx, ry, rz, geom, alloc.tensor, img
+        geom = torch.empty(lib.r2x_voxel_geom_bytes(P), **u8)
+        img = torch.empty(lib.r2x_voxel_image_bytes(nx, ny, nz), **u8)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        grid_args = (nx, ny, nz, float(sVoxel_x), float(sVoxel_y), float(sVoxel_z), float(center_x), float(center_y),
+                     float(center_z))
+        in_args = (_ptr(means3D), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                   _ptr(cov3D_precomp), int(bool(prefiltered)))
+        if debug or P == 0:
+            alloc = _BinningAlloc(dev)
+            nr = C.c_int(0)
+            rc = lib.r2x_voxel_forward(stream, P, *grid_args, *in_args, vol.data_ptr(), _ptr(rx), _ptr(ry), _ptr(rz),
+                                       geom.data_ptr(), img.data_ptr(), alloc.cb, None, int(bool(debug)), C.byref(nr))
+            check(rc, "r2x_voxel_forward")
+            return nr.value, vol, rx, ry, rz, geom, alloc.tensor, img
+        # the instance count depends strongly on the voxel pitch: key the hint on the grid as well
+        key = ("voxel", dev.index, P, nx, ny, nz, round(float(sVoxel_x) / nx, 6))
+        status = _status_pair(dev)
+        cap = _Workspace.capacity(key, P, 8)
+        while True:
+            nbytes = lib.r2x_binning_bytes(cap)
+            _Workspace.cap_of_bytes[int(nbytes)] = cap
+            binning = torch.empty(nbytes, **u8)
+            rc = lib.r2x_voxel_forward_async(stream, P, *grid_args, *in_args, vol.data_ptr(), _ptr(rx), _ptr(ry),
+                                             _ptr(rz), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
+                                             status.data_ptr())
+            check(rc, "r2x_voxel_forward_async")
+            R, overflow = status.tolist()
+            _Workspace.update(key, R)
+            if not overflow:
+                break
+            cap = _Workspace.capacity(key, P, 8)
+    return R, vol, rx, ry, rz, geom, binning, img
 
 
 def voxelize_gaussians_backward(means3D, radii_x, radii_y, radii_z, scales, rotations, scale_modifier,
@@ -184,6 +267,7 @@ def voxelize_gaussians_backward(means3D, radii_x, radii_y, radii_z, scales, rota
         opts = dict(dtype=torch.float32, device=dev)
         g_op = torch.empty((P, 1), **opts); g_mean = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
         g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        R = _carved_capacity(binningBuffer, R)
         scratch = torch.empty(lib.r2x_voxel_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
         rc = lib.r2x_voxel_backward(
             torch.cuda.current_stream(dev).cuda_stream, P, int(R), int(nVoxel_x), int(nVoxel_y), int(nVoxel_z),

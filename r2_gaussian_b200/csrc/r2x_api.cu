@@ -87,6 +87,12 @@ VoxelState carve_voxel(const void* buf, int P) {
     return s;
 }
 
+// image buffer = ranges[T] followed by the work plan
+TilePlan carve_plan(const void* image_buf, int tiles, const BinningView& bv) {
+    char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2));
+    return plan_view(p, tiles, bv);
+}
+
 int sort_passes(int num_tiles) {
     int bits = 1;
     while ((1ll << bits) < (long long)num_tiles) ++bits;
@@ -149,11 +155,11 @@ __global__ void voxel_export_geom_kernel(int P, VoxelGeom geom, float* means3D_n
 }
 // keys[s] = (tile << 32) | float_bits(depth of point_list[s]); depth lives at float index depth_idx of
 // the Gaussian's record (record stride rec_stride float4).
-__global__ void export_keys_kernel(long long R, const uint32_t* sorted_tiles, const uint32_t* point_list,
-                                   const float4* rec, int rec_stride, int depth_vec, int depth_comp, uint64_t* keys,
-                                   uint32_t* point_list_out) {
+__global__ void export_keys_kernel(long long R, const uint32_t* d_total, const uint32_t* sorted_tiles,
+                                   const uint32_t* point_list, const float4* rec, int rec_stride, int depth_vec,
+                                   int depth_comp, uint64_t* keys, uint32_t* point_list_out) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= R) return;
+    if (s >= R || s >= (long long)*d_total) return;   // R = carve capacity, *d_total = live instances
     const uint32_t g = point_list[s];
     if (keys) {
         const float4 v = rec[(size_t)rec_stride * g + depth_vec];
@@ -222,7 +228,9 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
     R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, s.geom.gx, s.geom.gy, tiles,
                           s.status, bv, R_launch, ranges));
     R2X_TRY(debug_sync(st, debug, "raster binning"));
-    R2X_TRY(launch_raster_render(st, W, H, s.geom, ranges, bv.point_list, out_color));
+    const TilePlan plan = carve_plan(image_buf, tiles, bv);
+    R2X_TRY(launch_plan(st, ranges, plan));
+    R2X_TRY(launch_raster_render(st, W, H, s.geom, ranges, bv.point_list, plan, R_launch, out_color));
     R2X_TRY(debug_sync(st, debug, "raster render"));
     return 0;
 }
@@ -281,7 +289,9 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
     R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, vg.gx, vg.gy, tiles, s.status, bv,
                           R_launch, ranges));
     R2X_TRY(debug_sync(st, debug, "voxel binning"));
-    R2X_TRY(launch_voxel_render(st, vg, s.geom, ranges, bv.point_list, out_volume));
+    const TilePlan plan = carve_plan(image_buf, tiles, bv);
+    R2X_TRY(launch_plan(st, ranges, plan));
+    R2X_TRY(launch_voxel_render(st, vg, s.geom, ranges, bv.point_list, plan, R_launch, out_volume));
     R2X_TRY(debug_sync(st, debug, "voxel render"));
     return 0;
 }
@@ -299,12 +309,12 @@ int r2x_version(void) { return 100; }
 size_t r2x_raster_geom_bytes(int P) { return raster_geom_bytes(P); }
 size_t r2x_raster_image_bytes(int W, int H) {
     size_t t = (size_t)((W + R2X_TILE - 1) / R2X_TILE) * ((H + R2X_TILE - 1) / R2X_TILE);
-    return al(t * sizeof(uint2)) + 512;
+    return al(t * sizeof(uint2)) + plan_bytes((int)t) + 512;
 }
 size_t r2x_voxel_geom_bytes(int P) { return voxel_geom_bytes(P); }
 size_t r2x_voxel_image_bytes(int nx, int ny, int nz) {
     size_t t = (size_t)((nx + 7) / 8) * ((ny + 7) / 8) * ((nz + 7) / 8);
-    return al(t * sizeof(uint2)) + 512;
+    return al(t * sizeof(uint2)) + plan_bytes((int)t) + 512;
 }
 size_t r2x_binning_bytes(long long R) { return binning_bytes(R); }
 size_t r2x_raster_bwd_scratch_bytes(long long R) { return al((size_t)(R > 0 ? R : 1) * 32) + 256; }
@@ -343,8 +353,10 @@ int r2x_raster_render_only(void* stream, int P, int W, int H, long long R, const
         return fail_msg(R2X_ERR_INVALID, "r2x_raster_render_only: bad args");
     RasterState s = carve_raster(geom_buf, P, W, H);
     BinningView bv = binning_view((void*)binning_buf, R);
-    return launch_raster_render((cudaStream_t)stream, W, H, s.geom, (const uint2*)al((size_t)image_buf), bv.point_list,
-                                out_color);
+    const uint2* ranges = (const uint2*)al((size_t)image_buf);
+    const TilePlan plan = carve_plan(image_buf, s.geom.gx * s.geom.gy, bv);
+    R2X_TRY(launch_plan((cudaStream_t)stream, ranges, plan));
+    return launch_raster_render((cudaStream_t)stream, W, H, s.geom, ranges, bv.point_list, plan, R, out_color);
 }
 
 int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long R, const void* geom_buf,
@@ -354,8 +366,10 @@ int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long
     const VoxelGrid vg = make_voxel_grid(nx, ny, nz, 1.f, 1.f, 1.f, 0.f, 0.f, 0.f);  // render needs the tile grid only
     VoxelState s = carve_voxel(geom_buf, P);
     BinningView bv = binning_view((void*)binning_buf, R);
-    return launch_voxel_render((cudaStream_t)stream, vg, s.geom, (const uint2*)al((size_t)image_buf), bv.point_list,
-                               out_volume);
+    const uint2* ranges = (const uint2*)al((size_t)image_buf);
+    const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
+    R2X_TRY(launch_plan((cudaStream_t)stream, ranges, plan));
+    return launch_voxel_render((cudaStream_t)stream, vg, s.geom, ranges, bv.point_list, plan, R, out_volume);
 }
 
 int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const float* means3D, const float* scales,
@@ -377,7 +391,8 @@ int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const fl
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
-    if (R > 0) R2X_TRY(launch_raster_render_bwd(st, W, H, s.geom, ranges, bv.point_list, dL_dpix, inst_grad));
+    const TilePlan plan = carve_plan(image_buf, s.geom.gx * s.geom.gy, bv);
+    if (R > 0) R2X_TRY(launch_raster_render_bwd(st, W, H, s.geom, ranges, bv.point_list, plan, R, dL_dpix, inst_grad));
     R2X_TRY(debug_sync(st, debug, "raster render backward"));
     R2X_TRY(launch_raster_gauss_bwd(st, P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
                                     projmatrix, W, H, tan_fovx, tan_fovy, mode, s.geom, R, bv.inst_pos, inst_grad,
@@ -407,7 +422,7 @@ int r2x_raster_export(void* stream, int P, int W, int H, long long R, const void
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
         const uint32_t* sorted = bv.keys[sort_passes(tiles) & 1];
-        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
@@ -456,7 +471,8 @@ int r2x_voxel_backward(void* stream, int P, long long R, int nx, int ny, int nz,
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
-    if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, dL_dvol, inst_grad));
+    const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
+    if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, plan, R, dL_dvol, inst_grad));
     R2X_TRY(debug_sync(st, debug, "voxel render backward"));
     R2X_TRY(launch_voxel_gauss_bwd(st, P, radii_x, radii_y, radii_z, scales, scale_modifier, rotations, cov3D_precomp, vg,
                                    s.geom, R, bv.inst_pos, inst_grad, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dscale,
@@ -479,7 +495,7 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
         const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
-        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, sorted, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;

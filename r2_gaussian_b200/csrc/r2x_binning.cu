@@ -5,10 +5,13 @@ namespace r2x {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static size_t plan_items(long long R) { return (size_t)(R > 0 ? R : 1) / PLAN_CHUNK + 1; }
+
 size_t binning_bytes(long long R) {
     size_t r = (size_t)(R > 0 ? R : 1);
     size_t per = align_up(r * sizeof(uint32_t), 256);
-    return 7 * per + align_up(256 * SORT_MAX_BLOCKS * sizeof(uint32_t), 256) + 256;
+    return 7 * per + align_up(256 * SORT_MAX_BLOCKS * sizeof(uint32_t), 256) +
+           align_up(plan_items(R) * sizeof(uint2), 256) + align_up(plan_items(R) * 512 * sizeof(float), 256) + 256;
 }
 
 BinningView binning_view(void* buf, long long R) {
@@ -23,9 +26,93 @@ BinningView binning_view(void* buf, long long R) {
     v.inst_g = (uint32_t*)p; p += per;
     v.point_list = (uint32_t*)p; p += per;
     v.inst_pos = (uint32_t*)p; p += per;
-    v.hist = (uint32_t*)p;
+    v.hist = (uint32_t*)p; p += align_up(256 * SORT_MAX_BLOCKS * sizeof(uint32_t), 256);
+    v.extra_item = (uint2*)p; p += align_up(plan_items(R) * sizeof(uint2), 256);
+    v.partial = (float*)p;
     v.capacity = R;
     return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Work plan (one CTA; T is at most a few 10^4)
+// ------------------------------------------------------------------------------------------------
+size_t plan_bytes(int num_tiles) {
+    size_t t = (size_t)num_tiles;
+    return align_up((t + 1) * sizeof(uint32_t), 256) + align_up(t * sizeof(uint32_t), 256) + 512;
+}
+
+TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
+    TilePlan pl;
+    size_t t = (size_t)num_tiles;
+    char* p = (char*)align_up((size_t)buf, 256);
+    pl.extra_off = (uint32_t*)p; p += align_up((t + 1) * sizeof(uint32_t), 256);
+    pl.tile_done = (uint32_t*)p; p += align_up(t * sizeof(uint32_t), 256);
+    pl.counter = (uint32_t*)p;
+    pl.extra_item = bv.extra_item;
+    pl.partial = bv.partial;
+    pl.num_tiles = num_tiles;
+    pl.max_extra = (long long)plan_items(bv.capacity);
+    return pl;
+}
+
+__global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ranges, TilePlan pl) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int T = pl.num_tiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    if (tid < 4) pl.counter[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        uint32_t a = 0;
+        if (t < T) {
+            const uint2 r = ranges[t];
+            const uint32_t n = r.y - r.x;
+            a = n ? (n - 1) / PLAN_CHUNK : 0u;  // extra chunks beyond the first
+            pl.tile_done[t] = 0;
+        }
+        uint32_t ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= o) ia += ta;
+        }
+        if (lane == 31) s_w[warp] = ia;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t x = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t tx = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += tx;
+            }
+            s_w[lane] = x - w;
+        }
+        __syncthreads();
+        const uint32_t ea = s_carry + s_w[warp] + ia - a;
+        if (t < T) {
+            pl.extra_off[t] = ea;
+            for (uint32_t c = 0; c < a; ++c)
+                if ((long long)(ea + c) < pl.max_extra) pl.extra_item[ea + c] = make_uint2((uint32_t)t, c + 1);
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = ea + a;
+        __syncthreads();
+    }
+    if (tid == 0) pl.extra_off[T] = s_carry;
+}
+
+int launch_plan(cudaStream_t st, const uint2* ranges, const TilePlan& plan) {
+    plan_kernel<<<1, 1024, 0, st>>>(ranges, plan);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int reset_plan_counter(cudaStream_t st, const TilePlan& plan, int which) {
+    R2X_CUDA_OK(cudaMemsetAsync(plan.counter + which, 0, sizeof(uint32_t), st));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,38 +282,59 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t*
     hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan of n = 256*nb uint32 in place, one CTA of 1024 threads
+// exclusive scan of n = 256*nb uint32 in place, one CTA of 1024 threads walking the table in coalesced
+// chunks of 4096 (one uint4 per thread) with a running carry
 __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int n) {
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = tid * per;
-    const int hi = min(lo + per, n);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += hist[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane], wi = w;
+    for (int base = 0; base < n; base += 4096) {
+        const int i = base + tid * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i + 3 < n) v = *reinterpret_cast<const uint4*>(hist + i);
+        else {
+            if (i < n) v.x = hist[i];
+            if (i + 1 < n) v.y = hist[i + 1];
+            if (i + 2 < n) v.z = hist[i + 2];
+        }
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        s_warp[lane] = wi - w;
-    }
-    __syncthreads();
-    uint32_t run = s_warp[warp] + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        uint32_t t = hist[i];
-        hist[i] = run;
-        run += t;
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        uint32_t run = carry + s_warp[warp] + incl - sum;
+        uint4 o4;
+        o4.x = run; run += v.x;
+        o4.y = run; run += v.y;
+        o4.z = run; run += v.z;
+        o4.w = run; run += v.w;
+        if (i + 3 < n) *reinterpret_cast<uint4*>(hist + i) = o4;
+        else {
+            if (i < n) hist[i] = o4.x;
+            if (i + 1 < n) hist[i + 1] = o4.y;
+            if (i + 2 < n) hist[i + 2] = o4.z;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;
+        __syncthreads();
     }
 }
 

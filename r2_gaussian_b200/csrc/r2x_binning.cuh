@@ -27,6 +27,8 @@ struct BinningView {
     uint32_t* point_list;  // [R] Gaussian id at sorted position s
     uint32_t* inst_pos;    // [R] sorted position of original instance i
     uint32_t* hist;        // [256 * SORT_MAX_BLOCKS] digit-major per-block histograms
+    uint2* extra_item;     // TilePlan::extra_item
+    float* partial;        // TilePlan::partial
     long long capacity;    // instances the buffer can hold
 };
 
@@ -34,6 +36,39 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;                         // keys per thread per sub-chunk
 constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096
 constexpr int SORT_MAX_BLOCKS = 296;                   // 2 CTAs per SM on 148 SMs
+
+// ---- work plan for the per-tile kernels -------------------------------------------------------
+// Per-tile lists are cut into chunks of PLAN_CHUNK instances; a (tile, chunk) pair is one work item of
+// the render kernels, handed out through an atomic counter, so that SM load is balanced no matter how
+// uneven the per-tile counts are.  Items [0,T) are chunk 0 of every tile (also of empty tiles: they
+// write the zeros); items [T, T+E) are the extra chunks, looked up in `extra_item`.  A tile with several
+// chunks combines its partial sums in chunk order (the last-arriving CTA does it) => deterministic.
+constexpr int PLAN_CHUNK = 256;
+struct TilePlan {
+    uint32_t* extra_off;  // [T+1] exclusive scan of (chunks_t - 1); [T] = E
+    uint32_t* tile_done;  // [T]   arrival counters of multi-chunk tiles
+    uint32_t* counter;    // [4]   work-queue heads (0: forward, 1: backward)
+    uint2* extra_item;    // [R/PLAN_CHUNK + 1] (tile, chunk >= 1) of extra item j   (binning buffer)
+    float* partial;       // [R/PLAN_CHUNK + 1][512] partial sums of extra chunks      (binning buffer)
+    int num_tiles;
+    long long max_extra;  // entries in extra_item / partial
+};
+size_t plan_bytes(int num_tiles);
+struct BinningView;
+TilePlan plan_view(void* image_buf_after_ranges, int num_tiles, const BinningView& bv);
+int launch_plan(cudaStream_t st, const uint2* ranges, const TilePlan& plan);
+int reset_plan_counter(cudaStream_t st, const TilePlan& plan, int which);
+
+__device__ __forceinline__ void plan_decode(const TilePlan& pl, const uint2* __restrict__ ranges, uint32_t item,
+                                            int& tile, int& chunk, int& nch, uint32_t& begin, int& n) {
+    if ((int)item < pl.num_tiles) { tile = (int)item; chunk = 0; }
+    else { const uint2 e = pl.extra_item[item - pl.num_tiles]; tile = (int)e.x; chunk = (int)e.y; }
+    nch = (int)(pl.extra_off[tile + 1] - pl.extra_off[tile]) + 1;
+    const uint2 r = ranges[tile];
+    begin = r.x + (uint32_t)chunk * PLAN_CHUNK;
+    const int left = (int)(r.y - r.x) - chunk * PLAN_CHUNK;
+    n = left < PLAN_CHUNK ? (left > 0 ? left : 0) : PLAN_CHUNK;
+}
 
 size_t binning_bytes(long long R);
 BinningView binning_view(void* buf, long long R);

@@ -1,6 +1,7 @@
 // r2x_raster.cuh -- launchers for the detector-image (X-ray projection) kernels.
 #pragma once
 #include "r2x_common.cuh"
+#include "r2x_binning.cuh"
 
 namespace r2x {
 
@@ -19,9 +20,10 @@ int launch_raster_preprocess(cudaStream_t st, int P, const float* means, const f
                              const float* proj, int W, int H, float tan_fovx, float tan_fovy, int mode,
                              int prefiltered, int* radii, const RasterGeom& geom);
 int launch_raster_render(cudaStream_t st, int W, int H, const RasterGeom& geom, const uint2* ranges,
-                         const uint32_t* point_list, float* out_color);
+                         const uint32_t* point_list, const TilePlan& plan, long long R_launch, float* out_color);
 int launch_raster_render_bwd(cudaStream_t st, int W, int H, const RasterGeom& geom, const uint2* ranges,
-                             const uint32_t* point_list, const float* dL_dpix, float4* inst_grad);
+                             const uint32_t* point_list, const TilePlan& plan, long long R_launch,
+                             const float* dL_dpix, float4* inst_grad);
 int launch_raster_gauss_bwd(cudaStream_t st, int P, const float* means, const int* radii, const float* scales,
                             float scale_modifier, const float* rots, const float* cov3D_precomp, const float* view,
                             const float* proj, int W, int H, float tan_fovx, float tan_fovy, int mode,

@@ -154,66 +154,92 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward render
+// forward render: persistent CTAs pull (tile, chunk) work items from the atomic queue of r2x_binning.cuh
 // ------------------------------------------------------------------------------------------------
 constexpr int VR_THREADS = 256;
-constexpr int VR_BATCH = 256;
 constexpr int VR_SLICES = 4;
+static_assert(PLAN_CHUNK == VR_THREADS, "one staged record per thread");
+
+struct VWorkItem {
+    int tile, chunk, nch, n;
+    uint32_t begin;
+    bool valid;
+};
+
+__device__ __forceinline__ VWorkItem vfetch_item(const TilePlan& pl, const uint2* __restrict__ ranges, uint32_t item,
+                                                 uint32_t total) {
+    VWorkItem w;
+    w.valid = item < total;
+    w.tile = 0; w.chunk = 0; w.nch = 1; w.n = 0; w.begin = 0;
+    if (w.valid) plan_decode(pl, ranges, item, w.tile, w.chunk, w.nch, w.begin, w.n);
+    return w;
+}
+
+__device__ __forceinline__ void vaccum_if(float& acc, float al, float p, float thr) {
+    asm("{\n"
+        ".reg .pred p1, p2;\n"
+        "setp.gt.f32 p1, %2, 0f00000000;\n"
+        "setp.geu.and.f32 p2, %1, %3, !p1;\n"
+        "@p2 add.f32 %0, %0, %1;\n"
+        "}\n"
+        : "+f"(acc)
+        : "f"(al), "f"(p), "f"(thr));
+}
 
 __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
                                                                   const uint32_t* __restrict__ point_list,
-                                                                  const float4* __restrict__ rec,
+                                                                  const float4* __restrict__ rec, TilePlan pl,
                                                                   float* __restrict__ out_volume) {
-    __shared__ __align__(16) float4 s_rec[2][VR_BATCH][3];       // 24 KB
-    __shared__ __align__(16) float s_red[VR_SLICES - 1][64][8];  // 6 KB
+    __shared__ __align__(16) float4 s_rec[2][VR_THREADS][3];      // 24 KB
+    __shared__ __align__(16) float s_red[VR_SLICES - 1][64][8];   // 6 KB
+    __shared__ uint32_t s_next;
+    __shared__ uint32_t s_last;
 
     const int tid = threadIdx.x;
     const int slice = tid >> 6, q = tid & 63;
     const int lx = q >> 3, ly = q & 7;
-    const int tile = blockIdx.x;
-    const int tx = tile % vg.gx, ty = (tile / vg.gx) % vg.gy, tz = tile / (vg.gx * vg.gy);
-    const float fx = (float)(tx * R2X_VTILE + lx) + 0.5f;
-    const float fy = (float)(ty * R2X_VTILE + ly) + 0.5f;
-    const float fz0 = (float)(tz * R2X_VTILE) + 0.5f;
+    const uint32_t total = (uint32_t)pl.num_tiles + pl.extra_off[pl.num_tiles];
 
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const int nbatches = (n + VR_BATCH - 1) / VR_BATCH;
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (tid == 0) s_next = atomicAdd(&pl.counter[0], 2u);
+    __syncthreads();
+    const uint32_t first = s_next;
+    __syncthreads();
+    VWorkItem A = vfetch_item(pl, ranges, first, total);
+    VWorkItem B = vfetch_item(pl, ranges, first + 1, total);
+    uint32_t idB = 0;
+    if (A.valid && tid < A.n) {
+        const uint32_t id = point_list[A.begin + tid];
+        cp_async16(&s_rec[0][tid][0], &rec[4 * (size_t)id]);
+        cp_async16(&s_rec[0][tid][1], &rec[4 * (size_t)id + 1]);
+        cp_async16(&s_rec[0][tid][2], &rec[4 * (size_t)id + 2]);
+    }
+    cp_async_commit();
+    if (B.valid && tid < B.n) idB = point_list[B.begin + tid];
+    int stage = 0;
 
-    uint32_t id_next = 0;
-    if (tid < n) id_next = point_list[range.x + tid];
-    if (nbatches > 0) {
-        if (tid < n) {
-            cp_async16(&s_rec[0][tid][0], &rec[4 * (size_t)id_next]);
-            cp_async16(&s_rec[0][tid][1], &rec[4 * (size_t)id_next + 1]);
-            cp_async16(&s_rec[0][tid][2], &rec[4 * (size_t)id_next + 2]);
+    while (A.valid) {
+        if (tid == 0) s_next = atomicAdd(&pl.counter[0], 1u);
+        if (B.valid && tid < B.n) {
+            cp_async16(&s_rec[stage ^ 1][tid][0], &rec[4 * (size_t)idB]);
+            cp_async16(&s_rec[stage ^ 1][tid][1], &rec[4 * (size_t)idB + 1]);
+            cp_async16(&s_rec[stage ^ 1][tid][2], &rec[4 * (size_t)idB + 2]);
         }
         cp_async_commit();
-        if (VR_BATCH + tid < n) id_next = point_list[range.x + VR_BATCH + tid];
-    }
-    for (int b = 0; b < nbatches; ++b) {
-        const int stage = b & 1;
-        if (b + 1 < nbatches) {
-            const int i1 = (b + 1) * VR_BATCH + tid;
-            if (i1 < n) {
-                cp_async16(&s_rec[stage ^ 1][tid][0], &rec[4 * (size_t)id_next]);
-                cp_async16(&s_rec[stage ^ 1][tid][1], &rec[4 * (size_t)id_next + 1]);
-                cp_async16(&s_rec[stage ^ 1][tid][2], &rec[4 * (size_t)id_next + 2]);
-            }
-            cp_async_commit();
-            const int i2 = (b + 2) * VR_BATCH + tid;
-            if (i2 < n) id_next = point_list[range.x + i2];
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        cp_async_wait<1>();
         __syncthreads();
-        const int nb = min(VR_BATCH, n - b * VR_BATCH);
+        VWorkItem Cw = vfetch_item(pl, ranges, s_next, total);
+        uint32_t idC = 0;
+        if (Cw.valid && tid < Cw.n) idC = point_list[Cw.begin + tid];
+
+        const int tx = A.tile % vg.gx, ty = (A.tile / vg.gx) % vg.gy, tz = A.tile / (vg.gx * vg.gy);
+        const float fx = (float)(tx * R2X_VTILE + lx) + 0.5f;
+        const float fy = (float)(ty * R2X_VTILE + ly) + 0.5f;
+        const float fz0 = (float)(tz * R2X_VTILE) + 0.5f;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
 #pragma unroll 2
-        for (int j = slice; j < nb; j += VR_SLICES) {
+        for (int j = slice; j < A.n; j += VR_SLICES) {
             const float4 r0 = s_rec[stage][j][0];  // px,py,pz,rho
             const float4 r1 = s_rec[stage][j][1];  // a2,b2,c2,d2
             const float4 r2 = s_rec[stage][j][2];  // e2,f2,depth,-
@@ -227,29 +253,64 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
                 const float u = fmaf(r2.y, dz, lin);
                 const float p = fmaf(dz, u, q0);  // = power * log2(e)
                 const float al = r0.w * ex2_approx(p);
-                if (!(p > 0.0f) && !(al < 0.000001f)) acc[k] += al;
+                vaccum_if(acc[k], al, p, 0.000001f);
             }
+        }
+        if (slice > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_red[slice - 1][q][k] = acc[k];
         }
         __syncthreads();
-    }
-    if (slice > 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s_red[slice - 1][q][k] = acc[k];
-    }
-    __syncthreads();
-    if (slice == 0) {
         const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z0 = tz * R2X_VTILE;
-        if (x < vg.nx && y < vg.ny) {
-            float* dst = out_volume + ((size_t)x * vg.ny + y) * vg.nz + z0;
+        const bool col_in = (x < vg.nx && y < vg.ny);
+        float* dst = out_volume + ((size_t)x * vg.ny + y) * vg.nz + z0;
+        if (slice == 0) {
+            float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float v = acc[k];
-                v += s_red[0][q][k];
-                v += s_red[1][q][k];
-                v += s_red[2][q][k];
-                if (z0 + k < vg.nz) dst[k] = v;
+                v[k] = acc[k];
+                v[k] += s_red[0][q][k];
+                v[k] += s_red[1][q][k];
+                v[k] += s_red[2][q][k];
+            }
+            if (A.chunk == 0) {
+                if (col_in) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (z0 + k < vg.nz) dst[k] = v[k];
+                }
+            } else {
+                const size_t slot = (size_t)(pl.extra_off[A.tile] + A.chunk - 1);
+                float4* ps = reinterpret_cast<float4*>(&pl.partial[slot * 512 + q * 8]);
+                ps[0] = make_float4(v[0], v[1], v[2], v[3]);
+                ps[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
+        if (A.nch > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(&pl.tile_done[A.tile], 1u) == (uint32_t)(A.nch - 1)) ? 1u : 0u;
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (slice == 0 && col_in) {
+                    const size_t base = (size_t)pl.extra_off[A.tile];
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = (z0 + k < vg.nz) ? __ldcg(&dst[k]) : 0.f;
+                    for (int c = 1; c < A.nch; ++c) {
+                        const float4* ps = reinterpret_cast<const float4*>(&pl.partial[(base + c - 1) * 512 + q * 8]);
+                        const float4 p0 = __ldcg(ps), p1 = __ldcg(ps + 1);
+                        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                        v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (z0 + k < vg.nz) dst[k] = v[k];
+                }
+            }
+        }
+        A = B; B = Cw; idB = idC; stage ^= 1;
     }
 }
 
@@ -258,26 +319,38 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list,
-                                                               const float4* __restrict__ rec,
+                                                               const float4* __restrict__ rec, TilePlan pl,
                                                                const float* __restrict__ dL_dvol,
                                                                float4* __restrict__ inst_grad) {
     __shared__ __align__(16) float s_dl[R2X_VTILE][R2X_VTILE][R2X_VTILE];
+    __shared__ uint32_t s_next;
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int tx = tile % vg.gx, ty = (tile / vg.gx) % vg.gy, tz = tile / (vg.gx * vg.gy);
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
-    if (n == 0) return;
-    for (int v = tid; v < 512; v += 256) {
-        const int lz = v & 7, ly = (v >> 3) & 7, lx = v >> 6;
-        const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z = tz * R2X_VTILE + lz;
-        s_dl[lx][ly][lz] = (x < vg.nx && y < vg.ny && z < vg.nz) ? dL_dvol[((size_t)x * vg.ny + y) * vg.nz + z] : 0.f;
-    }
-    __syncthreads();
-    const float fx0 = (float)(tx * R2X_VTILE) + 0.5f, fy0 = (float)(ty * R2X_VTILE) + 0.5f,
-                fz0 = (float)(tz * R2X_VTILE) + 0.5f;
-    for (int i = tid; i < n; i += 256) {
-        const uint32_t s = range.x + i;
+    const uint32_t total = (uint32_t)pl.num_tiles + pl.extra_off[pl.num_tiles];
+    int cur_tile = -1;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(&pl.counter[1], 1u);
+        __syncthreads();
+        const uint32_t item = s_next;
+        if (item >= total) break;
+        int tile, chunk, nch, n;
+        uint32_t begin;
+        plan_decode(pl, ranges, item, tile, chunk, nch, begin, n);
+        if (n == 0) continue;
+        const int tx = tile % vg.gx, ty = (tile / vg.gx) % vg.gy, tz = tile / (vg.gx * vg.gy);
+        if (tile != cur_tile) {
+            for (int v = tid; v < 512; v += 256) {
+                const int lz = v & 7, ly = (v >> 3) & 7, lx = v >> 6;
+                const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z = tz * R2X_VTILE + lz;
+                s_dl[lx][ly][lz] = (x < vg.nx && y < vg.ny && z < vg.nz) ? dL_dvol[((size_t)x * vg.ny + y) * vg.nz + z] : 0.f;
+            }
+            cur_tile = tile;
+        }
+        __syncthreads();
+        if (tid >= n) continue;
+        const float fx0 = (float)(tx * R2X_VTILE) + 0.5f, fy0 = (float)(ty * R2X_VTILE) + 0.5f,
+                    fz0 = (float)(tz * R2X_VTILE) + 0.5f;
+        const uint32_t s = begin + tid;
         const uint32_t g = point_list[s];
         const float4 r0 = rec[4 * (size_t)g];
         const float4 r1 = rec[4 * (size_t)g + 1];
@@ -438,18 +511,27 @@ int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const fl
     return 0;
 }
 
+static int vpersistent_grid(long long max_items) {
+    const long long cap = 148ll * 4;   // 4 CTAs of 256 threads per SM (54 registers/thread)
+    return (int)(max_items < cap ? (max_items > 0 ? max_items : 1) : cap);
+}
+
 int launch_voxel_render(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
-                        const uint32_t* point_list, float* out_volume) {
-    const int tiles = vg.gx * vg.gy * vg.gz;
-    voxel_render_kernel<<<tiles, VR_THREADS, 0, st>>>(vg, ranges, point_list, geom.rec, out_volume);
+                        const uint32_t* point_list, const TilePlan& plan, long long R_launch, float* out_volume) {
+    const long long items = (long long)plan.num_tiles + R_launch / PLAN_CHUNK + 1;
+    voxel_render_kernel<<<vpersistent_grid(items), VR_THREADS, 0, st>>>(vg, ranges, point_list, geom.rec, plan,
+                                                                        out_volume);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
-                            const uint32_t* point_list, const float* dL_dvol, float4* inst_grad) {
-    const int tiles = vg.gx * vg.gy * vg.gz;
-    voxel_render_bwd_kernel<<<tiles, 256, 0, st>>>(vg, ranges, point_list, geom.rec, dL_dvol, inst_grad);
+                            const uint32_t* point_list, const TilePlan& plan, long long R_launch,
+                            const float* dL_dvol, float4* inst_grad) {
+    const long long items = (long long)plan.num_tiles + R_launch / PLAN_CHUNK + 1;
+    R2X_CUDA_OK(cudaMemsetAsync(plan.counter + 1, 0, sizeof(uint32_t), st));
+    voxel_render_bwd_kernel<<<vpersistent_grid(items), 256, 0, st>>>(vg, ranges, point_list, geom.rec, plan, dL_dvol,
+                                                                     inst_grad);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }

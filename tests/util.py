@@ -71,7 +71,11 @@ def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None):
         keys = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
         pl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
-        rc = lib.r2x_raster_export(torch.cuda.current_stream().cuda_stream, P, W, H, R, geom.data_ptr(),
+        from r2_gaussian_b200._C import _carved_capacity
+        cap = _carved_capacity(binning, R)
+        keys = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+        pl = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        rc = lib.r2x_raster_export(torch.cuda.current_stream().cuda_stream, P, W, H, cap, geom.data_ptr(),
                                    binning.data_ptr() if binning.numel() else None, img.data_ptr(), xy.data_ptr(),
                                    depth.data_ptr(), co.data_ptr(), mu.data_ptr(), tt.data_ptr(), po.data_ptr(),
                                    keys.data_ptr(), pl.data_ptr(), ranges.data_ptr())
@@ -136,7 +140,11 @@ def ours_voxel_forward(cloud, nVoxel, sVoxel, center, export=True):
         keys = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
         pl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
-        rc = lib.r2x_voxel_export(torch.cuda.current_stream().cuda_stream, P, nx, ny, nz, R, geom.data_ptr(),
+        from r2_gaussian_b200._C import _carved_capacity
+        cap = _carved_capacity(binning, R)
+        keys = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+        pl = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        rc = lib.r2x_voxel_export(torch.cuda.current_stream().cuda_stream, P, nx, ny, nz, cap, geom.data_ptr(),
                                   binning.data_ptr() if binning.numel() else None, img.data_ptr(), xyz.data_ptr(),
                                   depth.data_ptr(), co.data_ptr(), tt.data_ptr(), po.data_ptr(), keys.data_ptr(),
                                   pl.data_ptr(), ranges.data_ptr())
