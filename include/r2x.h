@@ -57,9 +57,9 @@ int r2x_version(void);
 
 /* ---- buffer sizes -------------------------------------------------------------------------- */
 size_t r2x_raster_geom_bytes(int P);
-size_t r2x_raster_image_bytes(int W, int H);
+size_t r2x_raster_image_bytes(int P, int W, int H);
 size_t r2x_voxel_geom_bytes(int P);
-size_t r2x_voxel_image_bytes(int nx, int ny, int nz);
+size_t r2x_voxel_image_bytes(int P, int nx, int ny, int nz);
 size_t r2x_binning_bytes(long long R);             /* shared by rasterizer and voxelizer */
 size_t r2x_raster_bwd_scratch_bytes(long long R);  /* per-instance moment buffer of the backward pass */
 size_t r2x_voxel_bwd_scratch_bytes(long long R);

@@ -110,7 +110,7 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
         out_color = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty(lib.r2x_raster_geom_bytes(P), **u8)
-        img = torch.empty(lib.r2x_raster_image_bytes(W, H), **u8)
+        img = torch.empty(lib.r2x_raster_image_bytes(P, W, H), **u8)
         status = _status_pair(dev)
         key = ("raster", dev.index, P, W, H)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -219,7 +219,7 @@ def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3
         rx = torch.empty((P,), dtype=torch.int32, device=dev)
         ry = torch.empty_like(rx); rz = torch.empty_like(rx)
         geom = torch.empty(lib.r2x_voxel_geom_bytes(P), **u8)
-        img = torch.empty(lib.r2x_voxel_image_bytes(nx, ny, nz), **u8)
+        img = torch.empty(lib.r2x_voxel_image_bytes(P, nx, ny, nz), **u8)
         stream = torch.cuda.current_stream(dev).cuda_stream
         grid_args = (nx, ny, nz, float(sVoxel_x), float(sVoxel_y), float(sVoxel_z), float(center_x), float(center_y),
                      float(center_z))

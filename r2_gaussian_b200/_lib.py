@@ -22,9 +22,9 @@ PROTOTYPES = {
     "r2x_last_error": (C.c_char_p, []),
     "r2x_version": (_i, []),
     "r2x_raster_geom_bytes": (_sz, [_i]),
-    "r2x_raster_image_bytes": (_sz, [_i, _i]),
+    "r2x_raster_image_bytes": (_sz, [_i, _i, _i]),
     "r2x_voxel_geom_bytes": (_sz, [_i]),
-    "r2x_voxel_image_bytes": (_sz, [_i, _i, _i]),
+    "r2x_voxel_image_bytes": (_sz, [_i, _i, _i, _i]),
     "r2x_binning_bytes": (_sz, [_ll]),
     "r2x_raster_bwd_scratch_bytes": (_sz, [_ll]),
     "r2x_voxel_bwd_scratch_bytes": (_sz, [_ll]),

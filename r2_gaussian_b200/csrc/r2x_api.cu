@@ -87,10 +87,35 @@ VoxelState carve_voxel(const void* buf, int P) {
     return s;
 }
 
-// image buffer = ranges[T] followed by the work plan
+// image buffer = ranges[T] | work plan | direct-binning table (when T <= DIRECT_MAX_TILES)
 TilePlan carve_plan(const void* image_buf, int tiles, const BinningView& bv) {
     char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2));
     return plan_view(p, tiles, bv);
+}
+DirectBin carve_directbin(const void* image_buf, int P, int tiles) {
+    char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2)) + plan_bytes(tiles);
+    return directbin_view(p, P, tiles);
+}
+
+// sorted position -> tile id through the ranges (direct binning keeps no per-instance tile array)
+__global__ void export_keys_ranges_kernel(long long R, const uint32_t* d_total, const uint2* ranges, int T,
+                                          const uint32_t* point_list, const float4* rec, int rec_stride, int depth_vec,
+                                          int depth_comp, uint64_t* keys, uint32_t* point_list_out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= R || s >= (long long)*d_total) return;
+    const uint32_t g = point_list[s];
+    if (keys) {
+        int lo = 0, hi = T;   // largest tile with ranges[tile].x <= s among non-empty ones
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)ranges[mid].x <= s) lo = mid; else hi = mid;
+        }
+        while (lo > 0 && ranges[lo].x == ranges[lo].y) --lo;   // skip empty tiles sharing the same start
+        const float4 v = rec[(size_t)rec_stride * g + depth_vec];
+        const float d = depth_comp == 3 ? v.w : (depth_comp == 2 ? v.z : (depth_comp == 1 ? v.y : v.x));
+        keys[s] = ((uint64_t)(uint32_t)lo << 32) | (uint64_t)__float_as_uint(d);
+    }
+    if (point_list_out) point_list_out[s] = g;
 }
 
 int sort_passes(int num_tiles) {
@@ -203,11 +228,25 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
         return fail_msg(R2X_ERR_INVALID, "r2x_raster_forward: null input");
     if (!cov3D_precomp && (!scales || !rotations))
         return fail_msg(R2X_ERR_INVALID, "r2x_raster_forward: need scales+rotations or cov3D_precomp");
+    const bool direct = direct_ok(tiles);
+    DirectBin db{};
+    if (direct) {
+        db = carve_directbin(image_buf, P, tiles);
+        R2X_CUDA_OK(cudaMemsetAsync(db.done, 0, 8, st));
+    }
     R2X_TRY(launch_raster_preprocess(st, P, means3D, scales, scale_modifier, rotations, opacities, cov3D_precomp,
                                      viewmatrix, projmatrix, W, H, tan_fovx, tan_fovy, mode, prefiltered, radii,
-                                     s.geom));
+                                     s.geom, direct ? &db : nullptr));
     R2X_TRY(debug_sync(st, debug, "raster preprocess"));
-    R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
+    if (direct) {
+        // tile ranges, work plan and R come straight from the per-CTA tile histograms
+        BinningView none{};
+        const TilePlan plan0 = carve_plan(image_buf, tiles, none);
+        const long long cap0 = binning_alloc ? (1ll << 62) : capacity;
+        R2X_TRY(launch_direct_scan(st, db, ranges, plan0, s.status, cap0, binning_alloc ? nullptr : status_dev));
+    } else {
+        R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
+    }
     R2X_TRY(debug_sync(st, debug, "raster scan"));
     long long R_launch;
     if (binning_alloc) {  // synchronous variant: learn R, size the binning buffer exactly
@@ -223,13 +262,18 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
         if (!binning_buf || capacity < 0) return fail_msg(R2X_ERR_INVALID, "r2x_raster_forward_async: no binning buffer");
         R_launch = capacity;
     }
-    status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
     BinningView bv = binning_view(binning_buf, capacity);
-    R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, s.geom.gx, s.geom.gy, tiles,
-                          s.status, bv, R_launch, ranges));
-    R2X_TRY(debug_sync(st, debug, "raster binning"));
     const TilePlan plan = carve_plan(image_buf, tiles, bv);
-    R2X_TRY(launch_plan(st, ranges, plan));
+    if (direct) {
+        R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv,
+                                   s.geom.gx, s.geom.gy));
+    } else {
+        status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
+        R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, s.geom.gx, s.geom.gy, tiles,
+                              s.status, bv, R_launch, ranges));
+        R2X_TRY(launch_plan(st, ranges, plan));
+    }
+    R2X_TRY(debug_sync(st, debug, "raster binning"));
     R2X_TRY(launch_raster_render(st, W, H, s.geom, ranges, bv.point_list, plan, R_launch, out_color));
     R2X_TRY(debug_sync(st, debug, "raster render"));
     return 0;
@@ -266,10 +310,23 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
                         "r2x_voxel_forward: scales are required (the bounding radius is 3*max(scale)/dVoxel even "
                         "with cov3D_precomp; the reference dereferences scales unconditionally, VOX/forward.cu:137)");
     if (!cov3D_precomp && !rotations) return fail_msg(R2X_ERR_INVALID, "r2x_voxel_forward: need rotations or cov3D_precomp");
+    const bool direct = direct_ok(tiles);
+    DirectBin db{};
+    if (direct) {
+        db = carve_directbin(image_buf, P, tiles);
+        R2X_CUDA_OK(cudaMemsetAsync(db.done, 0, 8, st));
+    }
     R2X_TRY(launch_voxel_preprocess(st, P, means3D, scales, scale_modifier, rotations, opacities, cov3D_precomp, vg,
-                                    radii_x, radii_y, radii_z, s.geom));
+                                    radii_x, radii_y, radii_z, s.geom, direct ? &db : nullptr));
     R2X_TRY(debug_sync(st, debug, "voxel preprocess"));
-    R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
+    if (direct) {
+        BinningView none{};
+        const TilePlan plan0 = carve_plan(image_buf, tiles, none);
+        const long long cap0 = binning_alloc ? (1ll << 62) : capacity;
+        R2X_TRY(launch_direct_scan(st, db, ranges, plan0, s.status, cap0, binning_alloc ? nullptr : status_dev));
+    } else {
+        R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
+    }
     long long R_launch;
     if (binning_alloc) {
         uint32_t R = 0;
@@ -284,13 +341,18 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
         if (!binning_buf || capacity < 0) return fail_msg(R2X_ERR_INVALID, "r2x_voxel_forward_async: no binning buffer");
         R_launch = capacity;
     }
-    status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
     BinningView bv = binning_view(binning_buf, capacity);
-    R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, vg.gx, vg.gy, tiles, s.status, bv,
-                          R_launch, ranges));
-    R2X_TRY(debug_sync(st, debug, "voxel binning"));
     const TilePlan plan = carve_plan(image_buf, tiles, bv);
-    R2X_TRY(launch_plan(st, ranges, plan));
+    if (direct) {
+        R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv, vg.gx,
+                                   vg.gy));
+    } else {
+        status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
+        R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, vg.gx, vg.gy, tiles, s.status,
+                              bv, R_launch, ranges));
+        R2X_TRY(launch_plan(st, ranges, plan));
+    }
+    R2X_TRY(debug_sync(st, debug, "voxel binning"));
     R2X_TRY(launch_voxel_render(st, vg, s.geom, ranges, bv.point_list, plan, R_launch, out_volume));
     R2X_TRY(debug_sync(st, debug, "voxel render"));
     return 0;
@@ -307,14 +369,14 @@ const char* r2x_last_error(void) { return g_err.c_str(); }
 int r2x_version(void) { return 100; }
 
 size_t r2x_raster_geom_bytes(int P) { return raster_geom_bytes(P); }
-size_t r2x_raster_image_bytes(int W, int H) {
+size_t r2x_raster_image_bytes(int P, int W, int H) {
     size_t t = (size_t)((W + R2X_TILE - 1) / R2X_TILE) * ((H + R2X_TILE - 1) / R2X_TILE);
-    return al(t * sizeof(uint2)) + plan_bytes((int)t) + 512;
+    return al(t * sizeof(uint2)) + plan_bytes((int)t) + (direct_ok((int)t) ? directbin_bytes(P, (int)t) : 0) + 1024;
 }
 size_t r2x_voxel_geom_bytes(int P) { return voxel_geom_bytes(P); }
-size_t r2x_voxel_image_bytes(int nx, int ny, int nz) {
+size_t r2x_voxel_image_bytes(int P, int nx, int ny, int nz) {
     size_t t = (size_t)((nx + 7) / 8) * ((ny + 7) / 8) * ((nz + 7) / 8);
-    return al(t * sizeof(uint2)) + plan_bytes((int)t) + 512;
+    return al(t * sizeof(uint2)) + plan_bytes((int)t) + (direct_ok((int)t) ? directbin_bytes(P, (int)t) : 0) + 1024;
 }
 size_t r2x_binning_bytes(long long R) { return binning_bytes(R); }
 size_t r2x_raster_bwd_scratch_bytes(long long R) { return al((size_t)(R > 0 ? R : 1) * 32) + 256; }
@@ -421,8 +483,13 @@ int r2x_raster_export(void* stream, int P, int W, int H, long long R, const void
     if (ranges) R2X_CUDA_OK(cudaMemcpyAsync(ranges, (const void*)al((size_t)image_buf), sizeof(uint2) * tiles, cudaMemcpyDeviceToDevice, st));
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
-        const uint32_t* sorted = bv.keys[sort_passes(tiles) & 1];
-        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+        if (direct_ok(tiles)) {
+            export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
+                R, s.status, (const uint2*)al((size_t)image_buf), tiles, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+        } else {
+            const uint32_t* sorted = bv.keys[sort_passes(tiles) & 1];
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+        }
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
@@ -494,8 +561,13 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     if (ranges) R2X_CUDA_OK(cudaMemcpyAsync(ranges, (const void*)al((size_t)image_buf), sizeof(uint2) * tiles, cudaMemcpyDeviceToDevice, st));
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
-        const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
-        export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+        if (direct_ok((int)tiles)) {
+            export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
+                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+        } else {
+            const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+        }
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -432,6 +432,268 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Direct binning
+// ------------------------------------------------------------------------------------------------
+size_t directbin_bytes(int P, int num_tiles) {
+    const size_t nb = (size_t)((P > 0 ? P : 1) + DIRECT_BLOCK - 1) / DIRECT_BLOCK;
+    const size_t t = (size_t)num_tiles;
+    return align_up(t * nb * sizeof(uint32_t), 256) + align_up(t * sizeof(uint32_t), 256) +
+           align_up(nb * sizeof(uint32_t), 256) + 512;
+}
+
+DirectBin directbin_view(void* buf, int P, int num_tiles) {
+    DirectBin db;
+    const size_t nb = (size_t)((P > 0 ? P : 1) + DIRECT_BLOCK - 1) / DIRECT_BLOCK;
+    const size_t t = (size_t)num_tiles;
+    char* p = (char*)align_up((size_t)buf, 256);
+    db.table = (uint32_t*)p; p += align_up(t * nb * sizeof(uint32_t), 256);
+    db.tile_count = (uint32_t*)p; p += align_up(t * sizeof(uint32_t), 256);
+    db.block_total = (uint32_t*)p; p += align_up(nb * sizeof(uint32_t), 256);
+    db.done = (uint32_t*)p;
+    db.num_tiles = num_tiles;
+    db.nb = (int)nb;
+    return db;
+}
+
+// block-wide exclusive scan helper for the single finishing CTA (256 threads), arbitrary length, in order
+template <typename Load, typename Store>
+__device__ __forceinline__ uint32_t cta_exclusive_scan(int n, Load load, Store store, uint32_t* s_w, uint32_t* s_carry) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 256) {
+        const int i = base + tid;
+        const uint32_t a = i < n ? load(i) : 0u;
+        uint32_t ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= o) ia += t;
+        }
+        if (lane == 31) s_w[warp] = ia;
+        __syncthreads();
+        uint32_t wpre = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+            if (w < warp) wpre += s_w[w];
+        const uint32_t ex = *s_carry + wpre + ia - a;
+        if (i < n) store(i, ex, a);
+        __syncthreads();
+        if (tid == 255) *s_carry = ex + a;
+        __syncthreads();
+    }
+    return *s_carry;
+}
+
+// one warp per tile: exclusive prefix over the CTAs of that tile's column; last CTA builds ranges + plan
+__global__ void __launch_bounds__(256) direct_scan_kernel(DirectBin db, uint2* __restrict__ ranges, TilePlan pl,
+                                                          uint32_t* __restrict__ status, long long capacity,
+                                                          uint32_t* __restrict__ status_out) {
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_islast;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x * 8 + warp;
+    if (t < db.num_tiles) {
+        uint32_t* row = db.table + (size_t)t * db.nb;
+        uint32_t carry = 0;
+        for (int base = 0; base < db.nb; base += 32) {
+            const int i = base + lane;
+            const uint32_t a = i < db.nb ? row[i] : 0u;
+            uint32_t ia = a;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, ia, o);
+                if (lane >= o) ia += x;
+            }
+            if (i < db.nb) row[i] = carry + ia - a;
+            carry += __shfl_sync(0xffffffffu, ia, 31);
+        }
+        if (lane == 0) db.tile_count[t] = carry;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_islast = (atomicAdd(&db.done[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_islast) return;
+    __threadfence();
+    // ---- finishing CTA: tile ranges, work plan, CTA instance bases, status ----
+    const int T = db.num_tiles;
+    volatile uint32_t* tc = db.tile_count;
+    const uint32_t R = cta_exclusive_scan(
+        T, [&](int i) { return tc[i]; },
+        [&](int i, uint32_t ex, uint32_t a) { ranges[i] = make_uint2(ex, ex + a); pl.tile_done[i] = 0; }, s_w, &s_carry);
+    __syncthreads();
+    // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so publish EMPTY
+    // ranges -- the render then produces zeros without touching unwritten list entries -- and let the host
+    // see status[1] = 1 and re-run with a larger buffer.
+    const bool overflow = (long long)R > capacity;
+    if (overflow)
+        for (int i = tid; i < T; i += 256) ranges[i] = make_uint2(0u, 0u);
+    const uint32_t E = cta_exclusive_scan(
+        T, [&](int i) { const uint32_t n = overflow ? 0u : tc[i]; return n ? (n - 1) / PLAN_CHUNK : 0u; },
+        [&](int i, uint32_t ex, uint32_t) { pl.extra_off[i] = ex; }, s_w, &s_carry);
+    __syncthreads();
+    volatile uint32_t* bt = db.block_total;
+    cta_exclusive_scan(
+        db.nb, [&](int i) { return bt[i]; }, [&](int i, uint32_t ex, uint32_t) { db.block_total[i] = ex; }, s_w, &s_carry);
+    if (tid == 0) {
+        pl.extra_off[T] = E;
+        const uint32_t ov = ((long long)R > capacity) ? 1u : 0u;
+        status[0] = R;
+        status[1] = ov;
+        if (status_out) { status_out[0] = R; status_out[1] = ov; }
+    }
+    if (tid < 4) pl.counter[tid] = 0;
+}
+
+int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint2* ranges, const TilePlan& plan, uint32_t* status,
+                       long long capacity, uint32_t* status_out) {
+    direct_scan_kernel<<<(db.num_tiles + 7) / 8, 256, 0, st>>>(db, ranges, plan, status, capacity, status_out);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// CTA b regenerates the instances of Gaussians [256 b, 256 b + 256) in emission order and writes them to
+// their final positions.  Dynamic shared memory: base[T] u32 | tot[T] u16 | wcnt[8][T] u16.
+constexpr int FILL_ITEMS = 8;                       // instances per thread per sub-chunk
+constexpr int FILL_CHUNK = DIRECT_BLOCK * FILL_ITEMS;
+
+__global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const uint16_t* __restrict__ cube,
+                                                                   const uint32_t* __restrict__ tiles_touched,
+                                                                   uint32_t* __restrict__ offsets, DirectBin db,
+                                                                   const uint2* __restrict__ ranges, TilePlan pl,
+                                                                   uint32_t* __restrict__ point_list,
+                                                                   uint32_t* __restrict__ inst_pos, long long capacity,
+                                                                   int gx, int gy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = db.num_tiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int)blockIdx.x == db.nb) {   // extra CTA: (tile, chunk) table of the work plan
+        for (int t = tid; t < T; t += DIRECT_BLOCK) {
+            const uint32_t e0 = pl.extra_off[t], e1 = pl.extra_off[t + 1];
+            for (uint32_t c = 0; c < e1 - e0; ++c)
+                if ((long long)(e0 + c) < pl.max_extra) pl.extra_item[e0 + c] = make_uint2((uint32_t)t, c + 1);
+        }
+        return;
+    }
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* s_tot = reinterpret_cast<uint16_t*>(s_base + T);
+    uint16_t* s_wcnt = s_tot + T;    // [8][T]
+    __shared__ uint32_t s_loff[DIRECT_BLOCK + 1];
+    __shared__ uint32_t s_c01[DIRECT_BLOCK], s_c23[DIRECT_BLOCK], s_c45[DIRECT_BLOCK];
+    __shared__ uint32_t s_w8[8];
+
+    const int b = blockIdx.x;
+    const int g = b * DIRECT_BLOCK + tid;
+    uint32_t n = 0;
+    if (g < P) {
+        n = tiles_touched[g];
+        const uint32_t* c = reinterpret_cast<const uint32_t*>(cube + 6 * (size_t)g);
+        s_c01[tid] = c[0]; s_c23[tid] = c[1]; s_c45[tid] = c[2];
+    }
+    // CTA-exclusive scan of n
+    uint32_t ia = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += x;
+    }
+    if (lane == 31) s_w8[warp] = ia;
+    for (int t = tid; t < T; t += DIRECT_BLOCK) s_base[t] = ranges[t].x + db.table[(size_t)t * db.nb + b];
+    __syncthreads();
+    uint32_t wpre = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (w < warp) wpre += s_w8[w];
+    const uint32_t lex = wpre + ia - n;
+    s_loff[tid] = lex;
+    const uint32_t bbase = db.block_total[b];   // exclusive instance base of this CTA (after direct_scan)
+    if (tid == DIRECT_BLOCK - 1) s_loff[DIRECT_BLOCK] = lex + n;
+    if (g < P) offsets[g] = bbase + lex + n;     // inclusive scan, same meaning as the reference's point_offsets
+    __syncthreads();
+    const uint32_t total = s_loff[DIRECT_BLOCK];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t c0 = 0; c0 < total; c0 += FILL_CHUNK) {
+        for (int i = tid; i < 8 * T; i += DIRECT_BLOCK) s_wcnt[i] = 0;
+        __syncthreads();
+        uint32_t tl[FILL_ITEMS], gl[FILL_ITEMS];
+        uint16_t rk[FILL_ITEMS];
+        const uint32_t wb = c0 + (uint32_t)warp * (32 * FILL_ITEMS);
+#pragma unroll
+        for (int k = 0; k < FILL_ITEMS; ++k) {
+            const uint32_t j = wb + k * 32 + lane;
+            const bool valid = j < total;
+            uint32_t tile = 0xffffffffu, gloc = 0;
+            if (valid) {
+                // largest gloc with s_loff[gloc] <= j
+                int lo = 0, hi = DIRECT_BLOCK;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_loff[mid] <= j) lo = mid; else hi = mid;
+                }
+                gloc = (uint32_t)lo;
+                const uint32_t kk = j - s_loff[lo];
+                const uint32_t a = s_c01[lo], bb = s_c23[lo], cc = s_c45[lo];
+                const uint32_t x0 = a & 0xffff, y0 = a >> 16, z0 = bb & 0xffff, x1 = bb >> 16, y1 = cc & 0xffff;
+                const uint32_t w = x1 - x0, h = y1 - y0, wh = w * h;
+                const uint32_t z = kk / wh, r = kk - z * wh, y = r / w, x = r - y * w;
+                tile = ((z0 + z) * (uint32_t)gy + (y0 + y)) * (uint32_t)gx + (x0 + x);
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = s_wcnt[warp * T + tile];
+                s_wcnt[warp * T + tile] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            tl[k] = tile; gl[k] = gloc; rk[k] = (uint16_t)(old + __popc(peers & lt_mask));
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int t = tid; t < T; t += DIRECT_BLOCK) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t x = s_wcnt[w * T + t];
+                s_wcnt[w * T + t] = (uint16_t)run;
+                run += x;
+            }
+            s_tot[t] = (uint16_t)run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FILL_ITEMS; ++k) {
+            const uint32_t j = wb + k * 32 + lane;
+            if (j < total) {
+                const uint32_t pos = s_base[tl[k]] + s_wcnt[warp * T + tl[k]] + rk[k];
+                if ((long long)pos < capacity) point_list[pos] = (uint32_t)(b * DIRECT_BLOCK) + gl[k];
+                if ((long long)bbase + j < capacity) inst_pos[bbase + j] = pos;
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < T; t += DIRECT_BLOCK) s_base[t] += s_tot[t];
+        __syncthreads();
+    }
+}
+
+int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
+                       const DirectBin& db, const uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
+                       int gy) {
+    const size_t smem = (size_t)db.num_tiles * (4 + 2 + 16);
+    if (smem > 40 * 1024)
+        R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DIRECT_MAX_TILES * 22));
+    direct_fill_kernel<<<db.nb + 1, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
+                                                              bv.point_list, bv.inst_pos, bv.capacity, gx, gy);
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_sort_and_ranges(cudaStream_t st, long long R_launch, int num_tiles, const uint32_t* d_total,
                            const BinningView& bv, uint2* ranges, uint32_t** sorted_keys_out) {
     R2X_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, st));

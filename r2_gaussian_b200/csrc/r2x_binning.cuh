@@ -73,6 +73,64 @@ __device__ __forceinline__ void plan_decode(const TilePlan& pl, const uint2* __r
 size_t binning_bytes(long long R);
 BinningView binning_view(void* buf, long long R);
 
+// ---- direct binning (tile counts up to DIRECT_MAX_TILES) ----------------------------------------
+// No instance list is materialised and nothing is sorted.  The preprocess CTA b (256 consecutive
+// Gaussians) histograms its own instances per tile (`block_tile_histogram`, shared memory) into row b of
+// `table`; `direct_scan` turns every tile's column into exclusive prefixes over the CTAs (= where CTA b's
+// instances of tile t start inside the tile's list), derives the tile ranges, the CTA instance bases and
+// the work plan; `direct_fill` regenerates each CTA's instances in the reference's emission order and
+// writes the Gaussian ids straight to their final, stable positions.  4 kernels per forward in total.
+constexpr int DIRECT_MAX_TILES = 4096;
+constexpr int DIRECT_BLOCK = 256;       // Gaussians per preprocess CTA (== its thread count)
+struct DirectBin {
+    uint32_t* table;        // [T][nb]
+    uint32_t* tile_count;   // [T]
+    uint32_t* block_total;  // [nb]  instances of CTA b  -> exclusive base after direct_scan
+    uint32_t* done;         // [2]   CTA arrival counter of direct_scan
+    int num_tiles, nb;
+};
+size_t directbin_bytes(int P, int num_tiles);
+DirectBin directbin_view(void* buf, int P, int num_tiles);
+inline bool direct_ok(int num_tiles) { return num_tiles <= DIRECT_MAX_TILES; }
+
+// Called by all 256 threads of a preprocess CTA.  hist_s: shared uint32[T] scratch.  (c01,c23,c45) is
+// the packed tile cube of this thread's Gaussian, n its instance count (0 if culled).
+__device__ __forceinline__ void block_tile_histogram(uint32_t* hist_s, const DirectBin& db, uint32_t c01, uint32_t c23,
+                                                     uint32_t c45, uint32_t n, int gx, int gy) {
+    const int tid = threadIdx.x;
+    for (int t = tid; t < db.num_tiles; t += DIRECT_BLOCK) hist_s[t] = 0;
+    __syncthreads();
+    if (n) {
+        const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff,
+                       z1 = c45 >> 16;
+        for (uint32_t z = z0; z < z1; ++z)
+            for (uint32_t y = y0; y < y1; ++y) {
+                const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
+                for (uint32_t x = x0; x < x1; ++x) atomicAdd(&hist_s[rowb + x], 1u);
+            }
+    }
+    // block total of n (fixed-order tree, result identical for every thread that reads it)
+    __shared__ uint32_t s_wsum[DIRECT_BLOCK / 32];
+    uint32_t v = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) s_wsum[tid >> 5] = v;
+    __syncthreads();
+    for (int t = tid; t < db.num_tiles; t += DIRECT_BLOCK) db.table[(size_t)t * db.nb + blockIdx.x] = hist_s[t];
+    if (tid == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < DIRECT_BLOCK / 32; ++w) tot += s_wsum[w];
+        db.block_total[blockIdx.x] = tot;
+    }
+}
+
+int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint2* ranges, const TilePlan& plan, uint32_t* status,
+                       long long capacity, uint32_t* status_out);
+int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
+                       const DirectBin& db, const uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
+                       int gy);
+
 // Exclusive->inclusive scan of tiles_touched[P] into offsets[P]; total (R) is written to *d_total
 // (device) -- single pass, decoupled look-back.  scan_state needs scan_state_bytes(P) bytes, zeroed
 // by the call itself.

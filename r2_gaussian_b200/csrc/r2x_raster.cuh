@@ -18,7 +18,7 @@ struct RasterGeom {
 int launch_raster_preprocess(cudaStream_t st, int P, const float* means, const float* scales, float scale_modifier,
                              const float* rots, const float* opac, const float* cov3D_precomp, const float* view,
                              const float* proj, int W, int H, float tan_fovx, float tan_fovy, int mode,
-                             int prefiltered, int* radii, const RasterGeom& geom);
+                             int prefiltered, int* radii, const RasterGeom& geom, const DirectBin* db);
 int launch_raster_render(cudaStream_t st, int W, int H, const RasterGeom& geom, const uint2* ranges,
                          const uint32_t* point_list, const TilePlan& plan, long long R_launch, float* out_color);
 int launch_raster_render_bwd(cudaStream_t st, int W, int H, const RasterGeom& geom, const uint2* ranges,

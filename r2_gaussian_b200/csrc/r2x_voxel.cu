@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
     int P, const float* __restrict__ means, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ cov3D_precomp,
     VoxelGrid vg, int use_tma, int* __restrict__ radii_x, int* __restrict__ radii_y, int* __restrict__ radii_z,
-    VoxelGeom geom) {
+    VoxelGeom geom, DirectBin db, int direct) {
+    extern __shared__ __align__(16) uint32_t s_hist[];   // [T] when direct binning
     __shared__ __align__(16) float s_means[VPRE_THREADS * 3];
     __shared__ __align__(16) float s_scales[VPRE_THREADS * 3];
     __shared__ __align__(16) float4 s_rots[VPRE_THREADS];
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
     }
     __syncthreads();
     if (tma) mbar_wait(&s_bar, 0);
-    if (g >= P) return;
+    const bool live = g < P;
 
-    float mx, my, mz, s0, s1, s2, rho;
-    float4 q;
-    if (tma) {
+    float mx = 0.f, my = 0.f, mz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, rho = 0.f;
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (!live) {
+    } else if (tma) {
         mx = s_means[3 * tid]; my = s_means[3 * tid + 1]; mz = s_means[3 * tid + 2];
         rho = s_opac[tid];
         s0 = s_scales[3 * tid]; s1 = s_scales[3 * tid + 1]; s2 = s_scales[3 * tid + 2];
@@ -104,15 +106,16 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
     uint32_t ntiles = 0, c01 = 0, c23 = 0, c45 = 0;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
 
-    float c3[6];
-    if (cov3D_precomp) {
+    float c3[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!live) {
+    } else if (cov3D_precomp) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) c3[k] = cov3D_precomp[6 * (size_t)g + k];
     } else {
         cov3d_from_scale_rot(s0, s1, s2, scale_modifier, q, c3);
     }
     const VoxCov vc = voxel_cov(c3, vg.ix, vg.iy, vg.iz);
-    if (vc.det != 0.0f) {
+    if (live && vc.det != 0.0f) {
         float inv[6];
         voxel_inverse(vc, inv);
         const float ms3 = fmul(fmaxf(fmaxf(s0, s1), s2), 3.0f);
@@ -144,13 +147,16 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
             }
         }
     }
-    radii_x[g] = rxi; radii_y[g] = ryi; radii_z[g] = rzi;
-    geom.tiles_touched[g] = ntiles;
-    geom.rec[4 * (size_t)g + 0] = r0;
-    geom.rec[4 * (size_t)g + 1] = r1;
-    geom.rec[4 * (size_t)g + 2] = r2;
-    uint32_t* cu = reinterpret_cast<uint32_t*>(geom.cube + 6 * (size_t)g);
-    cu[0] = c01; cu[1] = c23; cu[2] = c45;
+    if (live) {
+        radii_x[g] = rxi; radii_y[g] = ryi; radii_z[g] = rzi;
+        geom.tiles_touched[g] = ntiles;
+        geom.rec[4 * (size_t)g + 0] = r0;
+        geom.rec[4 * (size_t)g + 1] = r1;
+        geom.rec[4 * (size_t)g + 2] = r2;
+        uint32_t* cu = reinterpret_cast<uint32_t*>(geom.cube + 6 * (size_t)g);
+        cu[0] = c01; cu[1] = c23; cu[2] = c45;
+    }
+    if (direct) block_tile_histogram(s_hist, db, c01, c23, c45, ntiles, vg.gx, vg.gy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,12 +507,16 @@ VoxelGrid make_voxel_grid(int nx, int ny, int nz, float sx, float sy, float sz, 
 
 int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const float* scales, float scale_modifier,
                             const float* rots, const float* opac, const float* cov3D_precomp, const VoxelGrid& vg,
-                            int* radii_x, int* radii_y, int* radii_z, const VoxelGeom& geom) {
+                            int* radii_x, int* radii_y, int* radii_z, const VoxelGeom& geom, const DirectBin* db) {
     if (P <= 0) return 0;
     auto al16 = [](const void* p) { return p && (((size_t)p) & 15) == 0; };
     const int use_tma = al16(means) && al16(opac) && al16(scales) && al16(rots);
-    voxel_preprocess_kernel<<<(P + VPRE_THREADS - 1) / VPRE_THREADS, VPRE_THREADS, 0, st>>>(
-        P, means, scales, scale_modifier, rots, opac, cov3D_precomp, vg, use_tma, radii_x, radii_y, radii_z, geom);
+    static_assert(VPRE_THREADS == DIRECT_BLOCK, "direct binning assumes one preprocess CTA per 256 Gaussians");
+    const DirectBin dbv = db ? *db : DirectBin{};
+    const size_t smem = db ? (size_t)db->num_tiles * sizeof(uint32_t) : 0;
+    voxel_preprocess_kernel<<<(P + VPRE_THREADS - 1) / VPRE_THREADS, VPRE_THREADS, smem, st>>>(
+        P, means, scales, scale_modifier, rots, opac, cov3D_precomp, vg, use_tma, radii_x, radii_y, radii_z, geom, dbv,
+        db ? 1 : 0);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }

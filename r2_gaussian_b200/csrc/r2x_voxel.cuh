@@ -25,7 +25,7 @@ VoxelGrid make_voxel_grid(int nx, int ny, int nz, float sx, float sy, float sz, 
 
 int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const float* scales, float scale_modifier,
                             const float* rots, const float* opac, const float* cov3D_precomp, const VoxelGrid& vg,
-                            int* radii_x, int* radii_y, int* radii_z, const VoxelGeom& geom);
+                            int* radii_x, int* radii_y, int* radii_z, const VoxelGeom& geom, const DirectBin* db);
 int launch_voxel_render(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
                         const uint32_t* point_list, const TilePlan& plan, long long R_launch, float* out_volume);
 int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,

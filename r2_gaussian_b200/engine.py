@@ -28,7 +28,7 @@ class RasterEngine:
         with torch.cuda.device(self.device):
             u8 = dict(dtype=torch.uint8, device=self.device)
             self.geom = torch.empty(self.lib.r2x_raster_geom_bytes(self.P), **u8)
-            self.img = torch.empty(self.lib.r2x_raster_image_bytes(self.W, self.H), **u8)
+            self.img = torch.empty(self.lib.r2x_raster_image_bytes(self.P, self.W, self.H), **u8)
             self.radii = torch.empty(self.P, dtype=torch.int32, device=self.device)
             self.out = torch.empty((1, self.H, self.W), dtype=torch.float32, device=self.device)
             self.status = torch.zeros(2, dtype=torch.int32, device=self.device)
@@ -94,7 +94,7 @@ class VoxelEngine:
         with torch.cuda.device(self.device):
             u8 = dict(dtype=torch.uint8, device=self.device)
             self.geom = torch.empty(self.lib.r2x_voxel_geom_bytes(self.P), **u8)
-            self.img = torch.empty(self.lib.r2x_voxel_image_bytes(self.nx, self.ny, self.nz), **u8)
+            self.img = torch.empty(self.lib.r2x_voxel_image_bytes(self.P, self.nx, self.ny, self.nz), **u8)
             self.radii = torch.empty((3, self.P), dtype=torch.int32, device=self.device)
             self.out = torch.empty((self.nx, self.ny, self.nz), dtype=torch.float32, device=self.device)
             self.status = torch.zeros(2, dtype=torch.int32, device=self.device)

@@ -46,8 +46,8 @@ def test_size_queries_and_error_path_without_gpu():
     assert lib.r2x_version() >= 100
     assert lib.r2x_raster_geom_bytes(1000) >= 1000 * (32 + 16 + 12 + 8)
     assert lib.r2x_binning_bytes(5000) >= 5000 * 28
-    assert lib.r2x_raster_image_bytes(512, 512) >= 1024 * 8
-    assert lib.r2x_voxel_image_bytes(256, 256, 256) >= 32768 * 8
+    assert lib.r2x_raster_image_bytes(1000, 512, 512) >= 1024 * 8
+    assert lib.r2x_voxel_image_bytes(1000, 256, 256, 256) >= 32768 * 8
     # invalid arguments are rejected before any CUDA call
     rc = lib.r2x_raster_forward_async(None, 10, 0, 16, None, None, None, 1.0, None, None, None, None, None, 1.0, 1.0, 0, 1,
                                       None, None, None, None, None, 0, None)

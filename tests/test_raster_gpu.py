@@ -11,7 +11,8 @@ import util
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["cone_init_small", "cone_trained_small", "parallel_trained_small", "cone_trained_ragged", "cone_trained_mid"]
+CASES = ["cone_init_small", "cone_trained_small", "parallel_trained_small", "cone_trained_ragged", "cone_trained_mid",
+         "cone_trained_bigdet"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -43,7 +44,7 @@ def test_forward_matches_oracle(name):
     assert err <= 1e-5 * scale + 1e-7, f"image error {err} vs scale {scale}"
 
 
-@pytest.mark.parametrize("name", ["cone_trained_small", "parallel_trained_small", "cone_trained_ragged"])
+@pytest.mark.parametrize("name", ["cone_trained_small", "parallel_trained_small", "cone_trained_ragged", "cone_trained_bigdet"])
 def test_backward_matches_oracle(name):
     cloud, view = util.case(name)
     ours = util.ours_raster_forward(cloud, view, export=False)
@@ -99,3 +100,32 @@ def test_cpu_tensor_is_rejected():
     with pytest.raises(RuntimeError):
         _C.rasterize_gaussians(torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4), 1.0,
                                torch.Tensor([]), torch.eye(4), torch.eye(4), 1.0, 1.0, 16, 16, torch.zeros(3), False, 1, False)
+
+
+def test_async_capacity_overflow_is_reported_and_recovered():
+    """The asynchronous C ABI never touches memory beyond the provisioned instance capacity; an
+    overflowing call reports it (status[1]) and the engine re-runs with a larger buffer."""
+    import torch
+    from r2_gaussian_b200.engine import RasterEngine, VoxelEngine
+
+    cloud, view = util.case("cone_trained_small")
+    t = util.to_torch(cloud, view)
+    ref = util.oracle_raster_forward(cloud, view)
+    eng = RasterEngine(cloud.P, view.image_width, view.image_height, "cuda", capacity=512)   # far too small
+    args = (t["means"], t["dens"], t["scales"], t["rots"], t["view"], t["proj"], t["campos"], view.tanfovx, view.tanfovy, view.mode)
+    eng.forward(*args)
+    assert eng.check() is False and eng.capacity >= ref["R"]
+    R = eng.fit(*args)
+    assert R == ref["R"]
+    img = eng.out[0].cpu().numpy()
+    assert np.abs(img.astype(np.float64) - ref["image"]).max() <= 1e-5 * np.abs(ref["image"]).max() + 1e-7
+    from r2_gaussian_b200 import scene
+    cl = scene.make_cloud(1500, kind="trained", seed=9)
+    tv = util.to_torch(cl, None)
+    vref = util.oracle_voxel_forward(cl, (32, 32, 32), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0))
+    ve = VoxelEngine(cl.P, (32, 32, 32), "cuda", capacity=1000)
+    vargs = (tv["means"], tv["dens"], tv["scales"], tv["rots"], (2.0, 2.0, 2.0), (0.0, 0.0, 0.0))
+    ve.forward(*vargs)
+    assert ve.check() is False
+    assert ve.fit(*vargs) == vref["R"]
+    assert np.abs(ve.out.cpu().numpy().astype(np.float64) - vref["vol"]).max() <= 1e-5 * np.abs(vref["vol"]).max() + 1e-7

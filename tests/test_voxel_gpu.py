@@ -12,6 +12,8 @@ GRIDS = {
     "ragged": ((20, 36, 28), (1.3, 2.0, 1.7), (0.1, -0.05, 0.2), 1200, "trained"),
     "tvcrop": ((32, 32, 32), (0.25, 0.25, 0.25), (0.31, -0.42, 0.13), 20000, "init"),   # train.py:128-139 style crop
     "full64": ((64, 64, 64), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0), 8000, "trained"),
+    # 18 x 17 x 17 = 5202 tiles > DIRECT_MAX_TILES: exercises the radix-sort binning path
+    "manytiles": ((144, 136, 136), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0), 1200, "trained"),
 }
 
 
@@ -39,7 +41,7 @@ def test_forward_matches_oracle(name):
     assert err <= 1e-5 * scale + 1e-7, f"volume error {err} vs scale {scale}"
 
 
-@pytest.mark.parametrize("name", ["full32", "ragged", "tvcrop"])
+@pytest.mark.parametrize("name", ["full32", "ragged", "tvcrop", "manytiles"])
 def test_backward_matches_oracle(name):
     nV, sV, ctr, P, kind = GRIDS[name]
     cloud = _cloud(P, kind, len(name))

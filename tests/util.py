@@ -22,6 +22,7 @@ def case(name: str):
         "cone_trained_ragged": ("trained", "cone", 1500, 100),   # detector not a multiple of 16
         "cone_trained_mid": ("trained", "cone", 20000, 256),
         "cone_init_mid": ("init", "cone", 50000, 256),
+        "cone_trained_bigdet": ("trained", "cone", 1500, 1040),  # 65 x 65 = 4225 tiles > DIRECT_MAX_TILES: radix path
     }[name]
     sc = scene.cone_beam_scanner(n, 64) if beam == "cone" else scene.parallel_beam_scanner(n, 64)
     view = scene.make_view(sc, 0.37 + 0.1 * len(name))
