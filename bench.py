@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_render * 1e3, "peak_source": peak_src,
                 "pair_evals_per_launch": pairs, "pair_evals_per_s": pairs / t_render,
-                "note": "kernel is FP32-issue/MUFU-bound (about 10.5 issue slots + 1 MUFU.EX2 per pixel-Gaussian "
+                "note": "kernel is FP32-issue/MUFU-bound (about 8.5 issue slots incl. 1 MUFU.EX2 per pixel-Gaussian "
                         "pair), not HBM-bound; see DESIGN.md section 5"}
 
     result = {
@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "num_rendered_mean": R_mean * 1.0, "api": "r2x_raster_forward_async (C ABI, no host sync)"},
         "value_warm_l2_back_to_back": args.steps / (warm_ms * 1e-3),
-        "gpu_launches": args.steps * 12,
+        "gpu_launches": args.steps * 4,  # preprocess(+tile histogram), direct_scan, direct_fill, render
         "roofline": roofline,
         "clocks": sampler.summary(),
     }

@@ -47,7 +47,7 @@ struct RasterState {
 
 size_t raster_geom_bytes(int P) {
     size_t p = (size_t)(P > 0 ? P : 1);
-    return al(p * 32) + al(p * 16) + al(p * 12) + 2 * al(p * 4) + al(scan_state_bytes((int)p)) + al(16) + 512;
+    return al(p * 32) + al(p * 16) + al(p * 12) + 3 * al(p * 4) + al(scan_state_bytes((int)p)) + al(16) + 512;
 }
 RasterState carve_raster(const void* buf, int P, int W, int H) {
     size_t p = (size_t)(P > 0 ? P : 1);
@@ -55,6 +55,7 @@ RasterState carve_raster(const void* buf, int P, int W, int H) {
     RasterState s;
     s.geom.rec = c.take<float4>(2 * p);
     s.geom.aux = c.take<float4>(p);
+    s.geom.depth = c.take<float>(p);
     s.geom.cube = c.take<uint16_t>(6 * p);
     s.geom.tiles_touched = c.take<uint32_t>(p);
     s.geom.offsets = c.take<uint32_t>(p);
@@ -99,8 +100,8 @@ DirectBin carve_directbin(const void* image_buf, int P, int tiles) {
 
 // sorted position -> tile id through the ranges (direct binning keeps no per-instance tile array)
 __global__ void export_keys_ranges_kernel(long long R, const uint32_t* d_total, const uint2* ranges, int T,
-                                          const uint32_t* point_list, const float4* rec, int rec_stride, int depth_vec,
-                                          int depth_comp, uint64_t* keys, uint32_t* point_list_out) {
+                                          const uint32_t* point_list, const float* depth, int depth_stride,
+                                          uint64_t* keys, uint32_t* point_list_out) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= R || s >= (long long)*d_total) return;
     const uint32_t g = point_list[s];
@@ -111,8 +112,7 @@ __global__ void export_keys_ranges_kernel(long long R, const uint32_t* d_total, 
             if ((long long)ranges[mid].x <= s) lo = mid; else hi = mid;
         }
         while (lo > 0 && ranges[lo].x == ranges[lo].y) --lo;   // skip empty tiles sharing the same start
-        const float4 v = rec[(size_t)rec_stride * g + depth_vec];
-        const float d = depth_comp == 3 ? v.w : (depth_comp == 2 ? v.z : (depth_comp == 1 ? v.y : v.x));
+        const float d = depth[(size_t)depth_stride * g];
         keys[s] = ((uint64_t)(uint32_t)lo << 32) | (uint64_t)__float_as_uint(d);
     }
     if (point_list_out) point_list_out[s] = g;
@@ -151,12 +151,12 @@ __global__ void raster_export_geom_kernel(int P, RasterGeom geom, float* means2D
     if (g >= P) return;
     const float4 r0 = geom.rec[2 * (size_t)g], r1 = geom.rec[2 * (size_t)g + 1], a = geom.aux[g];
     if (means2D) { means2D[2 * (size_t)g] = r0.x; means2D[2 * (size_t)g + 1] = r0.y; }
-    if (depths) depths[g] = r1.w;
+    if (depths) depths[g] = geom.depth[g];
     if (conic_opacity) {
         conic_opacity[4 * (size_t)g] = a.x; conic_opacity[4 * (size_t)g + 1] = a.y;
         conic_opacity[4 * (size_t)g + 2] = a.z; conic_opacity[4 * (size_t)g + 3] = a.w;
     }
-    if (mus) mus[g] = r0.w;
+    if (mus) mus[g] = r1.w;
     if (tiles_touched) tiles_touched[g] = geom.tiles_touched[g];
     if (point_offsets) point_offsets[g] = geom.offsets[g];
 }
@@ -181,14 +181,13 @@ __global__ void voxel_export_geom_kernel(int P, VoxelGeom geom, float* means3D_n
 // keys[s] = (tile << 32) | float_bits(depth of point_list[s]); depth lives at float index depth_idx of
 // the Gaussian's record (record stride rec_stride float4).
 __global__ void export_keys_kernel(long long R, const uint32_t* d_total, const uint32_t* sorted_tiles,
-                                   const uint32_t* point_list, const float4* rec, int rec_stride, int depth_vec,
-                                   int depth_comp, uint64_t* keys, uint32_t* point_list_out) {
+                                   const uint32_t* point_list, const float* depth, int depth_stride,
+                                   uint64_t* keys, uint32_t* point_list_out) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= R || s >= (long long)*d_total) return;   // R = carve capacity, *d_total = live instances
     const uint32_t g = point_list[s];
     if (keys) {
-        const float4 v = rec[(size_t)rec_stride * g + depth_vec];
-        const float d = depth_comp == 3 ? v.w : (depth_comp == 2 ? v.z : (depth_comp == 1 ? v.y : v.x));
+        const float d = depth[(size_t)depth_stride * g];
         keys[s] = ((uint64_t)sorted_tiles[s] << 32) | (uint64_t)__float_as_uint(d);
     }
     if (point_list_out) point_list_out[s] = g;
@@ -485,10 +484,10 @@ int r2x_raster_export(void* stream, int P, int W, int H, long long R, const void
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok(tiles)) {
             export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
-                R, s.status, (const uint2*)al((size_t)image_buf), tiles, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+                R, s.status, (const uint2*)al((size_t)image_buf), tiles, bv.point_list, s.geom.depth, 1, keys, point_list);
         } else {
             const uint32_t* sorted = bv.keys[sort_passes(tiles) & 1];
-            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 2, 1, 3, keys, point_list);
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.depth, 1, keys, point_list);
         }
     }
     R2X_CUDA_OK(cudaGetLastError());
@@ -563,10 +562,10 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok((int)tiles)) {
             export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
-                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
         } else {
             const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
-            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, s.geom.rec, 4, 2, 2, keys, point_list);
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
         }
     }
     R2X_CUDA_OK(cudaGetLastError());

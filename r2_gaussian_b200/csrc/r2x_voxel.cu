@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
                 ntiles = (uint32_t)nt;
                 r0 = make_float4(pvx, pvy, pvz, rho);
                 r1 = make_float4(inv[0] * (-0.5f * LOG2E), inv[1] * (-LOG2E), inv[2] * (-LOG2E), inv[3] * (-0.5f * LOG2E));
-                r2 = make_float4(inv[4] * (-LOG2E), inv[5] * (-0.5f * LOG2E), mz, 0.f);
+                // alpha = rho * 2^p >= 1e-6  <=>  p >= pmin; never for rho <= 0
+                const float pmin = (rho > 0.0f) ? (float)log2(1e-6 / (double)rho) : __int_as_float(0x7f800000);
+                r2 = make_float4(inv[4] * (-LOG2E), inv[5] * (-0.5f * LOG2E), mz, pmin);
                 c01 = (uint32_t)x0 | ((uint32_t)y0 << 16);
                 c23 = (uint32_t)z0 | ((uint32_t)x1 << 16);
                 c45 = (uint32_t)y1 | ((uint32_t)z1 << 16);
@@ -181,15 +183,16 @@ __device__ __forceinline__ VWorkItem vfetch_item(const TilePlan& pl, const uint2
     return w;
 }
 
-__device__ __forceinline__ void vaccum_if(float& acc, float al, float p, float thr) {
+// p1 = p > 0 ; p2 = !(p < pmin) && !p1 ; @p2 acc = fma(rho, e, acc)   (see r2x_raster.cu accum_if)
+__device__ __forceinline__ void vaccum_if(float& acc, float w, float e, float p, float pmin) {
     asm("{\n"
         ".reg .pred p1, p2;\n"
-        "setp.gt.f32 p1, %2, 0f00000000;\n"
-        "setp.geu.and.f32 p2, %1, %3, !p1;\n"
-        "@p2 add.f32 %0, %0, %1;\n"
+        "setp.gt.f32 p1, %3, 0f00000000;\n"
+        "setp.geu.and.f32 p2, %3, %4, !p1;\n"
+        "@p2 fma.rn.f32 %0, %1, %2, %0;\n"
         "}\n"
         : "+f"(acc)
-        : "f"(al), "f"(p), "f"(thr));
+        : "f"(w), "f"(e), "f"(p), "f"(pmin));
 }
 
 __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
@@ -258,8 +261,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
                 const float dz = dz0 - (float)k;
                 const float u = fmaf(r2.y, dz, lin);
                 const float p = fmaf(dz, u, q0);  // = power * log2(e)
-                const float al = r0.w * ex2_approx(p);
-                vaccum_if(acc[k], al, p, 0.000001f);
+                vaccum_if(acc[k], r0.w, ex2_approx(p), p, r2.w);
             }
         }
         if (slice > 0) {
@@ -382,8 +384,7 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
                     const float u = fmaf(r2.y, dz, lin);
                     const float p = fmaf(dz, u, q0);
                     const float G = ex2_approx(p);
-                    const float al = r0.w * G;
-                    const float t = (!(p > 0.0f) && !(al < 0.000001f)) ? dlv[k] * G : 0.f;
+                    const float t = (!(p > 0.0f) && !(p < r2.w)) ? dlv[k] * G : 0.f;
                     R0 += t;
                     const float tdz = t * dz;
                     Rz += tdz;
