@@ -7,7 +7,7 @@ namespace r2x {
 
 // Per-Gaussian projected state ("geometry buffer"), device pointers carved from the caller's buffer.
 struct RasterGeom {
-    float4* rec;              // [2P] (pix_x, pix_y, w = rho*mu, pmin = log2(1e-5/w)), (A,B,C scaled by -log2e/2,-log2e,-log2e/2, mu)
+    float4* rec;              // [2P] (pix_x, pix_y, log2(w = rho*mu), 0 [fast path] | w [exact path]), (A,B,C scaled by log2e/2, log2e, log2e/2, mu)
     float4* aux;              // [P]  (A, B, C, rho) raw conic + density (backward / parity export)
     float* depth;             // [P]  view-space depth (the low half of the reference's sort key)
     uint16_t* cube;           // [6P] tile rectangle x0,y0,0,x1,y1,1

@@ -139,10 +139,11 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
                 rxi = (int)rx; ryi = (int)ry; rzi = (int)rz;
                 ntiles = (uint32_t)nt;
                 r0 = make_float4(pvx, pvy, pvz, rho);
-                r1 = make_float4(inv[0] * (-0.5f * LOG2E), inv[1] * (-LOG2E), inv[2] * (-LOG2E), inv[3] * (-0.5f * LOG2E));
-                // alpha = rho * 2^p >= 1e-6  <=>  p >= pmin; never for rho <= 0
-                const float pmin = (rho > 0.0f) ? (float)log2(1e-6 / (double)rho) : __int_as_float(0x7f800000);
-                r2 = make_float4(inv[4] * (-LOG2E), inv[5] * (-0.5f * LOG2E), mz, pmin);
+                r1 = make_float4(inv[0] * (0.5f * LOG2E), inv[1] * LOG2E, inv[2] * LOG2E, inv[3] * (0.5f * LOG2E));
+                // q = -power*log2(e); contributes iff 0 <= q <= qmax = log2(rho/1e-6)  <=>  bits(q) < lim
+                const float qmax = (rho > 0.0f) ? (float)log2((double)rho / 1e-6) : -1.0f;
+                const uint32_t lim = (qmax >= 0.0f) ? (__float_as_uint(qmax) + 1u) : 0u;
+                r2 = make_float4(inv[4] * LOG2E, inv[5] * (0.5f * LOG2E), mz, __uint_as_float(lim));
                 c01 = (uint32_t)x0 | ((uint32_t)y0 << 16);
                 c23 = (uint32_t)z0 | ((uint32_t)x1 << 16);
                 c45 = (uint32_t)y1 | ((uint32_t)z1 << 16);
@@ -183,16 +184,15 @@ __device__ __forceinline__ VWorkItem vfetch_item(const TilePlan& pl, const uint2
     return w;
 }
 
-// p1 = p > 0 ; p2 = !(p < pmin) && !p1 ; @p2 acc = fma(rho, e, acc)   (see r2x_raster.cu accum_if)
-__device__ __forceinline__ void vaccum_if(float& acc, float w, float e, float p, float pmin) {
+// acc += w * e  iff  bits(q) < lim   (see r2x_raster.cu)
+__device__ __forceinline__ void vaccum_if(float& acc, float w, float e, float q, float lim) {
     asm("{\n"
-        ".reg .pred p1, p2;\n"
-        "setp.gt.f32 p1, %3, 0f00000000;\n"
-        "setp.geu.and.f32 p2, %3, %4, !p1;\n"
-        "@p2 fma.rn.f32 %0, %1, %2, %0;\n"
+        ".reg .pred p;\n"
+        "setp.lt.u32 p, %3, %4;\n"
+        "@p fma.rn.f32 %0, %1, %2, %0;\n"
         "}\n"
         : "+f"(acc)
-        : "f"(w), "f"(e), "f"(p), "f"(pmin));
+        : "f"(w), "f"(e), "r"(__float_as_uint(q)), "r"(__float_as_uint(lim)));
 }
 
 __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
             for (int k = 0; k < 8; ++k) {
                 const float dz = dz0 - (float)k;
                 const float u = fmaf(r2.y, dz, lin);
-                const float p = fmaf(dz, u, q0);  // = power * log2(e)
-                vaccum_if(acc[k], r0.w, ex2_approx(p), p, r2.w);
+                const float qq = fmaf(dz, u, q0);  // = -power * log2(e)
+                vaccum_if(acc[k], r0.w, ex2_approx(-qq), qq, r2.w);
             }
         }
         if (slice > 0) {
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
         const float4 r1 = rec[4 * (size_t)g + 1];
         const float4 r2 = rec[4 * (size_t)g + 2];
         float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
+        const uint32_t lim = __float_as_uint(r2.w);
         const float dz0 = r0.z - fz0;
 #pragma unroll 1
         for (int ix = 0; ix < R2X_VTILE; ++ix) {
@@ -382,9 +383,9 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
                 for (int k = 0; k < 8; ++k) {
                     const float dz = dz0 - (float)k;
                     const float u = fmaf(r2.y, dz, lin);
-                    const float p = fmaf(dz, u, q0);
-                    const float G = ex2_approx(p);
-                    const float t = (!(p > 0.0f) && !(p < r2.w)) ? dlv[k] * G : 0.f;
+                    const float qq = fmaf(dz, u, q0);
+                    const float G = ex2_approx(-qq);
+                    const float t = (__float_as_uint(qq) < lim) ? dlv[k] * G : 0.f;
                     R0 += t;
                     const float tdz = t * dz;
                     Rz += tdz;
