@@ -173,7 +173,7 @@ __global__ void voxel_export_geom_kernel(int P, VoxelGeom geom, float* means3D_n
         const float L = 1.4426950408889634f;
         float* co = conic_opacity + 7 * (size_t)g;
         co[0] = r1.x / (0.5f * L); co[1] = r1.y / L; co[2] = r1.z / L; co[3] = r1.w / (0.5f * L);
-        co[4] = r2.x / L; co[5] = r2.y / (0.5f * L); co[6] = r0.w;
+        co[4] = r2.x / L; co[5] = r2.y / (0.5f * L); co[6] = geom.rec[4 * (size_t)g + 3].x;
     }
     if (tiles_touched) tiles_touched[g] = geom.tiles_touched[g];
     if (point_offsets) point_offsets[g] = geom.offsets[g];

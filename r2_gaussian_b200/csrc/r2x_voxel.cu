@@ -138,12 +138,20 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
             if (nt != 0) {
                 rxi = (int)rx; ryi = (int)ry; rzi = (int)rz;
                 ntiles = (uint32_t)nt;
-                r0 = make_float4(pvx, pvy, pvz, rho);
+                // exponent-2 domain (see r2x_raster.cu): q = -power*log2(e) - log2(rho), alpha = 2^-q,
+                // alpha >= 1e-6 <=> q <= log2(1e6).  r2.w = 0: fast path (forward differences along z, no
+                // power test -- valid for a positive-definite conic); r2.w = rho: exact path.
+                const float lw = (rho > 0.0f) ? (float)log2((double)rho) : -__int_as_float(0x7f800000);
+                const float F2 = inv[5] * (0.5f * LOG2E);
+                const float m01 = inv[0] * inv[3] - inv[1] * inv[1];
+                const float det3 = inv[0] * (inv[3] * inv[5] - inv[4] * inv[4]) - inv[1] * (inv[1] * inv[5] - inv[4] * inv[2]) +
+                                   inv[2] * (inv[1] * inv[4] - inv[3] * inv[2]);
+                const bool pd = (inv[0] > 0.0f) && (inv[3] > 0.0f) && (inv[5] > 0.0f) && (m01 > 1e-4f * inv[0] * inv[3]) &&
+                                (det3 > 1e-4f * inv[0] * inv[3] * inv[5]);
+                const bool fast = !(rho > 0.0f) || (pd && F2 <= 2.0f);
+                r0 = make_float4(pvx, pvy, pvz, lw);
                 r1 = make_float4(inv[0] * (0.5f * LOG2E), inv[1] * LOG2E, inv[2] * LOG2E, inv[3] * (0.5f * LOG2E));
-                // q = -power*log2(e); contributes iff 0 <= q <= qmax = log2(rho/1e-6)  <=>  bits(q) < lim
-                const float qmax = (rho > 0.0f) ? (float)log2((double)rho / 1e-6) : -1.0f;
-                const uint32_t lim = (qmax >= 0.0f) ? (__float_as_uint(qmax) + 1u) : 0u;
-                r2 = make_float4(inv[4] * LOG2E, inv[5] * (0.5f * LOG2E), mz, __uint_as_float(lim));
+                r2 = make_float4(inv[4] * LOG2E, F2, mz, fast ? 0.0f : rho);
                 c01 = (uint32_t)x0 | ((uint32_t)y0 << 16);
                 c23 = (uint32_t)z0 | ((uint32_t)x1 << 16);
                 c45 = (uint32_t)y1 | ((uint32_t)z1 << 16);
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
         geom.rec[4 * (size_t)g + 0] = r0;
         geom.rec[4 * (size_t)g + 1] = r1;
         geom.rec[4 * (size_t)g + 2] = r2;
+        geom.rec[4 * (size_t)g + 3] = make_float4(rho, 0.f, 0.f, 0.f);   // backward / export only (never gathered)
         uint32_t* cu = reinterpret_cast<uint32_t*>(geom.cube + 6 * (size_t)g);
         cu[0] = c01; cu[1] = c23; cu[2] = c45;
     }
@@ -184,15 +193,54 @@ __device__ __forceinline__ VWorkItem vfetch_item(const TilePlan& pl, const uint2
     return w;
 }
 
-// acc += w * e  iff  bits(q) < lim   (see r2x_raster.cu)
-__device__ __forceinline__ void vaccum_if(float& acc, float w, float e, float q, float lim) {
+constexpr float VQ_CUT = 19.931568569324174f;   // log2(1e6): alpha = 2^-q >= 1e-6  <=>  q <= VQ_CUT
+
+__device__ __forceinline__ void vadd_if_le(float& acc, float e, float q) {
     asm("{\n"
         ".reg .pred p;\n"
-        "setp.lt.u32 p, %3, %4;\n"
-        "@p fma.rn.f32 %0, %1, %2, %0;\n"
+        "setp.le.f32 p, %2, %3;\n"
+        "@p add.f32 %0, %0, %1;\n"
         "}\n"
         : "+f"(acc)
-        : "f"(w), "f"(e), "r"(__float_as_uint(q)), "r"(__float_as_uint(lim)));
+        : "f"(e), "f"(q), "f"(VQ_CUT));
+}
+
+// 8 voxels of one z column.  q(k) = q0 + lin*dz + F2*dz^2 with dz = dz0 - k, minus log2 rho.
+__device__ __forceinline__ void voxel_fast_8(float (&acc)[8], const float4 r0, const float4 r1, const float4 r2,
+                                             float fx, float fy, float fz0) {
+    const float dx = r0.x - fx, dy = r0.y - fy, dz0 = r0.z - fz0;
+    const float q0 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), fmaf(r1.w * dy, dy, -r0.w));
+    const float lin = fmaf(r1.z, dx, r2.x * dy);
+    const float a2 = r2.y + r2.y;
+    const float e0 = r2.y - lin;                      // d(k) = e0 - a2 (dz0 - k)
+#pragma unroll
+    for (int h4 = 0; h4 < 2; ++h4) {
+        const float dza = dz0 - (float)(4 * h4);
+        float q = fmaf(dza, fmaf(r2.y, dza, lin), q0);
+        float d = fmaf(-a2, dza, e0);
+        vadd_if_le(acc[4 * h4], ex2_approx(-q), q);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            q += d;
+            d += a2;
+            vadd_if_le(acc[4 * h4 + k], ex2_approx(-q), q);
+        }
+    }
+}
+
+__device__ __forceinline__ void voxel_exact_8(float (&acc)[8], const float4 r0, const float4 r1, const float4 r2,
+                                              float fx, float fy, float fz0) {
+    const float dx = r0.x - fx, dy = r0.y - fy, dz0 = r0.z - fz0;
+    const float q0 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), (r1.w * dy) * dy);
+    const float lin = fmaf(r1.z, dx, r2.x * dy);
+    const float qmax = VQ_CUT + r0.w;
+    const uint32_t lim = (qmax >= 0.0f) ? (__float_as_uint(qmax) + 1u) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float dz = dz0 - (float)k;
+        const float q = fmaf(dz, fmaf(r2.y, dz, lin), q0);   // = -power * log2(e)
+        if (__float_as_uint(q) < lim) acc[k] = fmaf(r2.w, ex2_approx(-q), acc[k]);
+    }
 }
 
 __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
@@ -235,7 +283,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
         }
         cp_async_commit();
         cp_async_wait<1>();
-        __syncthreads();
+        const int any_exact = __syncthreads_or((tid < A.n) && (s_rec[stage][tid][2].w != 0.0f));
         VWorkItem Cw = vfetch_item(pl, ranges, s_next, total);
         uint32_t idC = 0;
         if (Cw.valid && tid < Cw.n) idC = point_list[Cw.begin + tid];
@@ -247,21 +295,15 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        if (!any_exact) {
 #pragma unroll 2
-        for (int j = slice; j < A.n; j += VR_SLICES) {
-            const float4 r0 = s_rec[stage][j][0];  // px,py,pz,rho
-            const float4 r1 = s_rec[stage][j][1];  // a2,b2,c2,d2
-            const float4 r2 = s_rec[stage][j][2];  // e2,f2,depth,-
-            const float dx = r0.x - fx, dy = r0.y - fy;
-            const float q0 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), (r1.w * dy) * dy);
-            const float lin = fmaf(r1.z, dx, r2.x * dy);
-            const float dz0 = r0.z - fz0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float dz = dz0 - (float)k;
-                const float u = fmaf(r2.y, dz, lin);
-                const float qq = fmaf(dz, u, q0);  // = -power * log2(e)
-                vaccum_if(acc[k], r0.w, ex2_approx(-qq), qq, r2.w);
+            for (int j = slice; j < A.n; j += VR_SLICES)
+                voxel_fast_8(acc, s_rec[stage][j][0], s_rec[stage][j][1], s_rec[stage][j][2], fx, fy, fz0);
+        } else {
+            for (int j = slice; j < A.n; j += VR_SLICES) {
+                const float4 r0 = s_rec[stage][j][0], r1 = s_rec[stage][j][1], r2 = s_rec[stage][j][2];
+                if (r2.w == 0.0f) voxel_fast_8(acc, r0, r1, r2, fx, fy, fz0);
+                else voxel_exact_8(acc, r0, r1, r2, fx, fy, fz0);
             }
         }
         if (slice > 0) {
@@ -364,7 +406,8 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
         const float4 r1 = rec[4 * (size_t)g + 1];
         const float4 r2 = rec[4 * (size_t)g + 2];
         float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
-        const uint32_t lim = __float_as_uint(r2.w);
+        const float qmax = VQ_CUT + r0.w;   // contributes iff 0 <= q <= log2(rho / 1e-6)
+        const uint32_t lim = (qmax >= 0.0f) ? (__float_as_uint(qmax) + 1u) : 0u;
         const float dz0 = r0.z - fz0;
 #pragma unroll 1
         for (int ix = 0; ix < R2X_VTILE; ++ix) {
@@ -437,7 +480,7 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
             Sxx += b.x; Sxy += b.y; Sxz += b.z; Syy += b.w;
             Syz += c.x; Szz += c.y;
         }
-        const float rho = geom.rec[4 * (size_t)g].w;
+        const float rho = geom.rec[4 * (size_t)g + 3].x;
         const bool have_sr = (cov3D_precomp == nullptr);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);

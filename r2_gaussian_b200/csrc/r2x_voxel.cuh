@@ -15,7 +15,7 @@ struct VoxelGrid {
 };
 
 struct VoxelGeom {
-    float4* rec;              // [4P] (px,py,pz,rho), (a,b,c,d scaled), (e,f scaled, depth, lim = bits(log2(rho/1e-6))+1), pad -> 64-byte stride
+    float4* rec;              // [4P] (px,py,pz,log2 rho), (a,b,c,d scaled), (e,f scaled, depth, 0 fast | rho exact), (rho,-,-,-)
     uint16_t* cube;           // [6P] x0,y0,z0,x1,y1,z1 tile cube
     uint32_t* tiles_touched;  // [P]
     uint32_t* offsets;        // [P]
