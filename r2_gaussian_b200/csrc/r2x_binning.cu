@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(
                     keys_out[pos] = key[k];
                     if (LAST) {
                         point_list[pos] = inst_g[v];
-                        inst_pos[v] = pos;
+                        inst_pos[pos] = v;
                     } else {
                         vals_out[pos] = v;
                     }
@@ -671,8 +671,10 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
             const uint32_t j = wb + k * 32 + lane;
             if (j < total) {
                 const uint32_t pos = s_base[tl[k]] + s_wcnt[warp * T + tl[k]] + rk[k];
-                if ((long long)pos < capacity) point_list[pos] = (uint32_t)(b * DIRECT_BLOCK) + gl[k];
-                if ((long long)bbase + j < capacity) inst_pos[bbase + j] = pos;
+                if ((long long)pos < capacity) {
+                    point_list[pos] = (uint32_t)(b * DIRECT_BLOCK) + gl[k];
+                    inst_pos[pos] = bbase + j;
+                }
             }
         }
         __syncthreads();

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list,
+                                                               const uint32_t* __restrict__ inst_pos,
                                                                const float4* __restrict__ rec, TilePlan pl,
                                                                const float* __restrict__ dL_dvol,
                                                                float4* __restrict__ inst_grad) {
@@ -445,9 +446,10 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
             Sxy = fmaf(dx, Xy, Sxy);
             Sxz = fmaf(dx, Xz, Sxz);
         }
-        inst_grad[3 * (size_t)s] = make_float4(S0, Sx, Sy, Sz);
-        inst_grad[3 * (size_t)s + 1] = make_float4(Sxx, Sxy, Sxz, Syy);
-        inst_grad[3 * (size_t)s + 2] = make_float4(Syz, Szz, 0.f, 0.f);
+        const uint32_t slot = inst_pos[s];   // emission-order index: a Gaussian's instances are contiguous there
+        inst_grad[3 * (size_t)slot] = make_float4(S0, Sx, Sy, Sz);
+        inst_grad[3 * (size_t)slot + 1] = make_float4(Sxx, Sxy, Sxz, Syy);
+        inst_grad[3 * (size_t)slot + 2] = make_float4(Syz, Szz, 0.f, 0.f);
     }
 }
 
@@ -470,12 +472,12 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
         const uint32_t n = geom.tiles_touched[g];
         const uint32_t start = geom.offsets[g] - n;
         float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sz = 0.f, Sxx = 0.f, Sxy = 0.f, Sxz = 0.f, Syy = 0.f, Syz = 0.f, Szz = 0.f;
-        for (uint32_t k = 0; k < n; ++k) {
-            if ((long long)start + k >= capacity) break;
-            const uint32_t s = inst_pos[start + k];
-            const float4 a = inst_grad[3 * (size_t)s];
-            const float4 b = inst_grad[3 * (size_t)s + 1];
-            const float4 c = inst_grad[3 * (size_t)s + 2];
+        const uint32_t nlive = ((long long)start + n <= capacity) ? n : 0u;
+#pragma unroll 4
+        for (uint32_t k = 0; k < nlive; ++k) {
+            const float4 a = inst_grad[3 * (size_t)(start + k)];
+            const float4 b = inst_grad[3 * (size_t)(start + k) + 1];
+            const float4 c = inst_grad[3 * (size_t)(start + k) + 2];
             S0 += a.x; Sx += a.y; Sy += a.z; Sz += a.w;
             Sxx += b.x; Sxy += b.y; Sxz += b.z; Syy += b.w;
             Syz += c.x; Szz += c.y;
@@ -581,12 +583,12 @@ int launch_voxel_render(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& g
 }
 
 int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
-                            const uint32_t* point_list, const TilePlan& plan, long long R_launch,
-                            const float* dL_dvol, float4* inst_grad) {
+                            const uint32_t* point_list, const uint32_t* inst_pos, const TilePlan& plan,
+                            long long R_launch, const float* dL_dvol, float4* inst_grad) {
     const long long items = (long long)plan.num_tiles + R_launch / PLAN_CHUNK + 1;
     R2X_CUDA_OK(cudaMemsetAsync(plan.counter + 1, 0, sizeof(uint32_t), st));
-    voxel_render_bwd_kernel<<<vpersistent_grid(items), 256, 0, st>>>(vg, ranges, point_list, geom.rec, plan, dL_dvol,
-                                                                     inst_grad);
+    voxel_render_bwd_kernel<<<vpersistent_grid(items), 256, 0, st>>>(vg, ranges, point_list, inst_pos, geom.rec, plan,
+                                                                     dL_dvol, inst_grad);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }

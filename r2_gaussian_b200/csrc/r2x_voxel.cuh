@@ -29,8 +29,8 @@ int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const fl
 int launch_voxel_render(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
                         const uint32_t* point_list, const TilePlan& plan, long long R_launch, float* out_volume);
 int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeom& geom, const uint2* ranges,
-                            const uint32_t* point_list, const TilePlan& plan, long long R_launch,
-                            const float* dL_dvol, float4* inst_grad);
+                            const uint32_t* point_list, const uint32_t* inst_pos, const TilePlan& plan,
+                            long long R_launch, const float* dL_dvol, float4* inst_grad);
 int launch_voxel_gauss_bwd(cudaStream_t st, int P, const int* radii_x, const int* radii_y, const int* radii_z,
                            const float* scales, float scale_modifier, const float* rots, const float* cov3D_precomp,
                            const VoxelGrid& vg, const VoxelGeom& geom, long long capacity, const uint32_t* inst_pos,
