@@ -231,7 +231,6 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
     DirectBin db{};
     if (direct) {
         db = carve_directbin(image_buf, P, tiles);
-        R2X_CUDA_OK(cudaMemsetAsync(db.done, 0, 8, st));
     }
     R2X_TRY(launch_raster_preprocess(st, P, means3D, scales, scale_modifier, rotations, opacities, cov3D_precomp,
                                      viewmatrix, projmatrix, W, H, tan_fovx, tan_fovy, mode, prefiltered, radii,
@@ -239,10 +238,8 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
     R2X_TRY(debug_sync(st, debug, "raster preprocess"));
     if (direct) {
         // tile ranges, work plan and R come straight from the per-CTA tile histograms
-        BinningView none{};
-        const TilePlan plan0 = carve_plan(image_buf, tiles, none);
         const long long cap0 = binning_alloc ? (1ll << 62) : capacity;
-        R2X_TRY(launch_direct_scan(st, db, ranges, plan0, s.status, cap0, binning_alloc ? nullptr : status_dev));
+        R2X_TRY(launch_direct_scan(st, db, s.status, cap0, binning_alloc ? nullptr : status_dev));
     } else {
         R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
     }
@@ -313,16 +310,13 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
     DirectBin db{};
     if (direct) {
         db = carve_directbin(image_buf, P, tiles);
-        R2X_CUDA_OK(cudaMemsetAsync(db.done, 0, 8, st));
     }
     R2X_TRY(launch_voxel_preprocess(st, P, means3D, scales, scale_modifier, rotations, opacities, cov3D_precomp, vg,
                                     radii_x, radii_y, radii_z, s.geom, direct ? &db : nullptr));
     R2X_TRY(debug_sync(st, debug, "voxel preprocess"));
     if (direct) {
-        BinningView none{};
-        const TilePlan plan0 = carve_plan(image_buf, tiles, none);
         const long long cap0 = binning_alloc ? (1ll << 62) : capacity;
-        R2X_TRY(launch_direct_scan(st, db, ranges, plan0, s.status, cap0, binning_alloc ? nullptr : status_dev));
+        R2X_TRY(launch_direct_scan(st, db, s.status, cap0, binning_alloc ? nullptr : status_dev));
     } else {
         R2X_TRY(launch_scan(st, P, s.geom.tiles_touched, s.geom.offsets, s.scan_state, s.status));
     }

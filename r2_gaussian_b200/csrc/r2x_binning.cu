@@ -450,7 +450,6 @@ DirectBin directbin_view(void* buf, int P, int num_tiles) {
     db.table = (uint32_t*)p; p += align_up(t * nb * sizeof(uint32_t), 256);
     db.tile_count = (uint32_t*)p; p += align_up(t * sizeof(uint32_t), 256);
     db.block_total = (uint32_t*)p; p += align_up(nb * sizeof(uint32_t), 256);
-    db.done = (uint32_t*)p;
     db.num_tiles = num_tiles;
     db.nb = (int)nb;
     return db;
@@ -486,113 +485,144 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(int n, Load load, Store s
     return *s_carry;
 }
 
-// one warp per tile: exclusive prefix over the CTAs of that tile's column; last CTA builds ranges + plan
-__global__ void __launch_bounds__(256) direct_scan_kernel(DirectBin db, uint2* __restrict__ ranges, TilePlan pl,
-                                                          uint32_t* __restrict__ status, long long capacity,
-                                                          uint32_t* __restrict__ status_out) {
-    __shared__ uint32_t s_w[8];
-    __shared__ uint32_t s_carry;
-    __shared__ uint32_t s_islast;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.x * 8 + warp;
-    if (t < db.num_tiles) {
-        uint32_t* row = db.table + (size_t)t * db.nb;
-        uint32_t carry = 0;
-        for (int base = 0; base < db.nb; base += 32) {
-            const int i = base + lane;
-            const uint32_t a = i < db.nb ? row[i] : 0u;
-            uint32_t ia = a;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xffffffffu, ia, o);
-                if (lane >= o) ia += x;
-            }
-            if (i < db.nb) row[i] = carry + ia - a;
-            carry += __shfl_sync(0xffffffffu, ia, 31);
+// Column scan of table[nb][T]: CTA = 32 tiles x 32 row segments (1024 threads); every thread sums its rows of
+// one tile column (coalesced 128-byte row pieces), the segment sums are scanned through shared memory, then the
+// rows are re-read (L2) and replaced by the exclusive prefix over the CTAs.  CTA 0 also publishes
+// R = sum of the CTA instance totals and the overflow flag.
+constexpr int SCAN_SEGS = 32;
+__global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_t* __restrict__ status,
+                                                           long long capacity, uint32_t* __restrict__ status_out) {
+    __shared__ uint32_t s_seg[SCAN_SEGS][33];
+    __shared__ uint32_t s_red[32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int T = db.num_tiles, nb = db.nb;
+    const int t = blockIdx.x * 32 + lane;
+    const int rps = (nb + SCAN_SEGS - 1) / SCAN_SEGS;
+    const int r0 = min(seg * rps, nb), r1 = min(r0 + rps, nb);
+    uint32_t sum = 0;
+    if (t < T) {
+        const uint32_t* col = db.table + t;
+        int r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            const uint32_t a0 = col[(size_t)r * T], a1 = col[(size_t)(r + 1) * T], a2 = col[(size_t)(r + 2) * T],
+                           a3 = col[(size_t)(r + 3) * T];
+            sum += (a0 + a1) + (a2 + a3);
         }
-        if (lane == 0) db.tile_count[t] = carry;
+        for (; r < r1; ++r) sum += col[(size_t)r * T];
     }
-    __threadfence();
+    s_seg[seg][lane] = sum;
     __syncthreads();
-    if (tid == 0) s_islast = (atomicAdd(&db.done[0], 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_islast) return;
-    __threadfence();
-    // ---- finishing CTA: tile ranges, work plan, CTA instance bases, status ----
-    const int T = db.num_tiles;
-    volatile uint32_t* tc = db.tile_count;
-    const uint32_t R = cta_exclusive_scan(
-        T, [&](int i) { return tc[i]; },
-        [&](int i, uint32_t ex, uint32_t a) { ranges[i] = make_uint2(ex, ex + a); pl.tile_done[i] = 0; }, s_w, &s_carry);
-    __syncthreads();
-    // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so publish EMPTY
-    // ranges -- the render then produces zeros without touching unwritten list entries -- and let the host
-    // see status[1] = 1 and re-run with a larger buffer.
-    const bool overflow = (long long)R > capacity;
-    if (overflow)
-        for (int i = tid; i < T; i += 256) ranges[i] = make_uint2(0u, 0u);
-    const uint32_t E = cta_exclusive_scan(
-        T, [&](int i) { const uint32_t n = overflow ? 0u : tc[i]; return n ? (n - 1) / PLAN_CHUNK : 0u; },
-        [&](int i, uint32_t ex, uint32_t) { pl.extra_off[i] = ex; }, s_w, &s_carry);
-    __syncthreads();
-    volatile uint32_t* bt = db.block_total;
-    cta_exclusive_scan(
-        db.nb, [&](int i) { return bt[i]; }, [&](int i, uint32_t ex, uint32_t) { db.block_total[i] = ex; }, s_w, &s_carry);
-    if (tid == 0) {
-        pl.extra_off[T] = E;
-        const uint32_t ov = ((long long)R > capacity) ? 1u : 0u;
-        status[0] = R;
-        status[1] = ov;
-        if (status_out) { status_out[0] = R; status_out[1] = ov; }
+    uint32_t pre = 0;
+    for (int k = 0; k < seg; ++k) pre += s_seg[k][lane];
+    if (t < T) {
+        if (seg == SCAN_SEGS - 1) db.tile_count[t] = pre + sum;
+        uint32_t* col = db.table + t;
+        int r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            const uint32_t a0 = col[(size_t)r * T], a1 = col[(size_t)(r + 1) * T], a2 = col[(size_t)(r + 2) * T],
+                           a3 = col[(size_t)(r + 3) * T];
+            col[(size_t)r * T] = pre;
+            col[(size_t)(r + 1) * T] = pre + a0;
+            col[(size_t)(r + 2) * T] = pre + a0 + a1;
+            col[(size_t)(r + 3) * T] = pre + a0 + a1 + a2;
+            pre += (a0 + a1) + (a2 + a3);
+        }
+        for (; r < r1; ++r) {
+            const uint32_t a = col[(size_t)r * T];
+            col[(size_t)r * T] = pre;
+            pre += a;
+        }
     }
-    if (tid < 4) pl.counter[tid] = 0;
+    if (blockIdx.x == 0) {
+        uint32_t v = 0;
+        for (int i = threadIdx.x; i < nb; i += 1024) v += db.block_total[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[seg] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t R = 0;
+            for (int w = 0; w < 32; ++w) R += s_red[w];
+            const uint32_t ov = ((long long)R > capacity) ? 1u : 0u;
+            status[0] = R;
+            status[1] = ov;
+            if (status_out) { status_out[0] = R; status_out[1] = ov; }
+        }
+    }
 }
 
-int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint2* ranges, const TilePlan& plan, uint32_t* status,
-                       long long capacity, uint32_t* status_out) {
-    direct_scan_kernel<<<(db.num_tiles + 7) / 8, 256, 0, st>>>(db, ranges, plan, status, capacity, status_out);
+int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, long long capacity,
+                       uint32_t* status_out) {
+    direct_scan_kernel<<<(db.num_tiles + 31) / 32, 1024, 0, st>>>(db, status, capacity, status_out);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// CTA b regenerates the instances of Gaussians [256 b, 256 b + 256) in emission order and writes them to
-// their final positions.  Dynamic shared memory: base[T] u32 | tot[T] u16 | wcnt[8][T] u16.
-constexpr int FILL_ITEMS = 8;                       // instances per thread per sub-chunk
-constexpr int FILL_CHUNK = DIRECT_BLOCK * FILL_ITEMS;
-
+// CTA b places the instances of Gaussians [256 b, 256 b + 256).  It marks, per tile, WHICH of its Gaussians
+// touch the tile (a 256-bit mask per tile, word w = warp w's 32 Gaussians); a thread per tile then walks the
+// set bits in ascending order = ascending Gaussian id, which is the stable order, and writes the ids to
+// range[t].x + prefix[b][t] + k.  No search, no division per instance, no warp match.  Every CTA derives the
+// tile ranges and its instance base itself (exclusive scans of tile_count / block_total: small and L2-hot),
+// so nothing serial sits between the column scan and this kernel.  The extra CTA (b == nb) publishes the
+// ranges and the work plan for the render.  Dynamic shared memory: mask[8][T] u32 | base[T] u32.
 __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const uint16_t* __restrict__ cube,
                                                                    const uint32_t* __restrict__ tiles_touched,
                                                                    uint32_t* __restrict__ offsets, DirectBin db,
-                                                                   const uint2* __restrict__ ranges, TilePlan pl,
+                                                                   uint2* __restrict__ ranges, TilePlan pl,
                                                                    uint32_t* __restrict__ point_list,
                                                                    uint32_t* __restrict__ inst_pos, long long capacity,
                                                                    int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_carry;
     const int T = db.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if ((int)blockIdx.x == db.nb) {   // extra CTA: (tile, chunk) table of the work plan
-        for (int t = tid; t < T; t += DIRECT_BLOCK) {
-            const uint32_t e0 = pl.extra_off[t], e1 = pl.extra_off[t + 1];
-            for (uint32_t c = 0; c < e1 - e0; ++c)
-                if ((long long)(e0 + c) < pl.max_extra) pl.extra_item[e0 + c] = make_uint2((uint32_t)t, c + 1);
+    const uint32_t* tc = db.tile_count;
+    if ((int)blockIdx.x == db.nb) {   // extra CTA: tile ranges + work plan
+        uint32_t* s_ex = reinterpret_cast<uint32_t*>(smem_raw);
+        const uint32_t R = cta_exclusive_scan(
+            T, [&](int i) { return tc[i]; }, [&](int i, uint32_t ex, uint32_t) { s_ex[i] = ex; }, s_w, &s_carry);
+        // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so publish EMPTY
+        // ranges -- the render then produces zeros without touching unwritten list entries -- and the host
+        // sees status[1] = 1 (direct_scan) and re-runs with a larger buffer.
+        const bool overflow = (long long)R > capacity;
+        for (int i = tid; i < T; i += DIRECT_BLOCK) {
+            const uint32_t ex = s_ex[i];
+            ranges[i] = overflow ? make_uint2(0u, 0u) : make_uint2(ex, ex + tc[i]);
+            pl.tile_done[i] = 0;
         }
+        __syncthreads();
+        const uint32_t E = cta_exclusive_scan(
+            T, [&](int i) { const uint32_t n = overflow ? 0u : tc[i]; return n ? (n - 1) / PLAN_CHUNK : 0u; },
+            [&](int i, uint32_t ex, uint32_t ne) {
+                pl.extra_off[i] = ex;
+                for (uint32_t c = 0; c < ne; ++c)
+                    if ((long long)(ex + c) < pl.max_extra) pl.extra_item[ex + c] = make_uint2((uint32_t)i, c + 1);
+            },
+            s_w, &s_carry);
+        if (tid == 0) pl.extra_off[T] = E;
+        if (tid < 4) pl.counter[tid] = 0;
         return;
     }
-    uint32_t* s_base = reinterpret_cast<uint32_t*>(smem_raw);
-    uint16_t* s_tot = reinterpret_cast<uint16_t*>(s_base + T);
-    uint16_t* s_wcnt = s_tot + T;    // [8][T]
-    __shared__ uint32_t s_loff[DIRECT_BLOCK + 1];
-    __shared__ uint32_t s_c01[DIRECT_BLOCK], s_c23[DIRECT_BLOCK], s_c45[DIRECT_BLOCK];
-    __shared__ uint32_t s_w8[8];
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);   // [8][T]
+    uint32_t* s_base = s_mask + 8 * (size_t)T;                   // [T]
+    __shared__ uint2 s_aw[DIRECT_BLOCK];   // per Gaussian: (slot of its first instance - index of its first tile, w | h << 16)
+    __shared__ uint32_t s_w8[8], s_bb[8];
 
     const int b = blockIdx.x;
     const int g = b * DIRECT_BLOCK + tid;
-    uint32_t n = 0;
+    for (int i = tid; i < 2 * T; i += DIRECT_BLOCK) reinterpret_cast<uint4*>(s_mask)[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t n = 0, c01 = 0, c23 = 0, c45 = 0;
     if (g < P) {
         n = tiles_touched[g];
         const uint32_t* c = reinterpret_cast<const uint32_t*>(cube + 6 * (size_t)g);
-        s_c01[tid] = c[0]; s_c23[tid] = c[1]; s_c45[tid] = c[2];
+        c01 = c[0]; c23 = c[1]; c45 = c[2];
     }
+    // instance base of this CTA = sum of the totals of the CTAs before it
+    uint32_t bsum = 0;
+    for (int i = tid; i < b; i += DIRECT_BLOCK) bsum += db.block_total[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     // CTA-exclusive scan of n
     uint32_t ia = n;
 #pragma unroll
@@ -601,95 +631,66 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
         if (lane >= o) ia += x;
     }
     if (lane == 31) s_w8[warp] = ia;
-    for (int t = tid; t < T; t += DIRECT_BLOCK) s_base[t] = ranges[t].x + db.table[(size_t)t * db.nb + b];
-    __syncthreads();
-    uint32_t wpre = 0;
+    if (lane == 0) s_bb[warp] = bsum;
+    // where this CTA's run starts inside every tile list
+    const uint32_t* row = db.table + (size_t)b * T;
+    const uint32_t R = cta_exclusive_scan(
+        T, [&](int i) { return tc[i]; }, [&](int i, uint32_t ex, uint32_t) { s_base[i] = ex + row[i]; }, s_w, &s_carry);
+    uint32_t wpre = 0, bbase = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w)
+    for (int w = 0; w < 8; ++w) {
         if (w < warp) wpre += s_w8[w];
+        bbase += s_bb[w];
+    }
     const uint32_t lex = wpre + ia - n;
-    s_loff[tid] = lex;
-    const uint32_t bbase = db.block_total[b];   // exclusive instance base of this CTA (after direct_scan)
-    if (tid == DIRECT_BLOCK - 1) s_loff[DIRECT_BLOCK] = lex + n;
     if (g < P) offsets[g] = bbase + lex + n;     // inclusive scan, same meaning as the reference's point_offsets
+    if ((long long)R > capacity) return;         // overflow: nothing may be written (uniform across the grid)
+    // mark
+    if (n) {
+        const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff,
+                       z1 = c45 >> 16;
+        // emission slot of instance (tx,ty,tz) = bbase + lex + ((tz-z0) h + (ty-y0)) w + (tx-x0)
+        //                                      = [bbase + lex - ((z0 h + y0) w + x0)] + (tz h + ty) w + tx   (mod 2^32)
+        const uint32_t w = x1 - x0, h = y1 - y0;
+        s_aw[tid] = make_uint2(bbase + lex - ((z0 * h + y0) * w + x0), w | (h << 16));
+        uint32_t* plane = s_mask + (size_t)warp * T;
+        const uint32_t bit = 1u << lane;
+        for (uint32_t z = z0; z < z1; ++z)
+            for (uint32_t y = y0; y < y1; ++y) {
+                const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
+                for (uint32_t x = x0; x < x1; ++x) atomicOr(&plane[rowb + x], bit);
+            }
+    }
     __syncthreads();
-    const uint32_t total = s_loff[DIRECT_BLOCK];
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    for (uint32_t c0 = 0; c0 < total; c0 += FILL_CHUNK) {
-        for (int i = tid; i < 8 * T; i += DIRECT_BLOCK) s_wcnt[i] = 0;
-        __syncthreads();
-        uint32_t tl[FILL_ITEMS], gl[FILL_ITEMS];
-        uint16_t rk[FILL_ITEMS];
-        const uint32_t wb = c0 + (uint32_t)warp * (32 * FILL_ITEMS);
+    // place
+    const uint32_t gxy = (uint32_t)gx * (uint32_t)gy;
+    for (int t = tid; t < T; t += DIRECT_BLOCK) {
+        uint32_t pos = s_base[t];
+        const uint32_t tz = (uint32_t)t / gxy, rem = (uint32_t)t - tz * gxy, ty = rem / (uint32_t)gx,
+                       tx = rem - ty * (uint32_t)gx;
 #pragma unroll
-        for (int k = 0; k < FILL_ITEMS; ++k) {
-            const uint32_t j = wb + k * 32 + lane;
-            const bool valid = j < total;
-            uint32_t tile = 0xffffffffu, gloc = 0;
-            if (valid) {
-                // largest gloc with s_loff[gloc] <= j
-                int lo = 0, hi = DIRECT_BLOCK;
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_loff[mid] <= j) lo = mid; else hi = mid;
-                }
-                gloc = (uint32_t)lo;
-                const uint32_t kk = j - s_loff[lo];
-                const uint32_t a = s_c01[lo], bb = s_c23[lo], cc = s_c45[lo];
-                const uint32_t x0 = a & 0xffff, y0 = a >> 16, z0 = bb & 0xffff, x1 = bb >> 16, y1 = cc & 0xffff;
-                const uint32_t w = x1 - x0, h = y1 - y0, wh = w * h;
-                const uint32_t z = kk / wh, r = kk - z * wh, y = r / w, x = r - y * w;
-                tile = ((z0 + z) * (uint32_t)gy + (y0 + y)) * (uint32_t)gx + (x0 + x);
-            }
-            const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (valid && lane == leader) {
-                old = s_wcnt[warp * T + tile];
-                s_wcnt[warp * T + tile] = (uint16_t)(old + __popc(peers));
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            tl[k] = tile; gl[k] = gloc; rk[k] = (uint16_t)(old + __popc(peers & lt_mask));
-            __syncwarp();
-        }
-        __syncthreads();
-        for (int t = tid; t < T; t += DIRECT_BLOCK) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const uint32_t x = s_wcnt[w * T + t];
-                s_wcnt[w * T + t] = (uint16_t)run;
-                run += x;
-            }
-            s_tot[t] = (uint16_t)run;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < FILL_ITEMS; ++k) {
-            const uint32_t j = wb + k * 32 + lane;
-            if (j < total) {
-                const uint32_t pos = s_base[tl[k]] + s_wcnt[warp * T + tl[k]] + rk[k];
-                if ((long long)pos < capacity) {
-                    point_list[pos] = (uint32_t)(b * DIRECT_BLOCK) + gl[k];
-                    inst_pos[pos] = bbase + j;
-                }
+        for (int w = 0; w < 8; ++w) {
+            uint32_t m = s_mask[(size_t)w * T + t];
+            while (m) {
+                const int bitpos = __ffs(m) - 1;
+                m &= m - 1;
+                const int gl = w * 32 + bitpos;
+                const uint2 aw = s_aw[gl];
+                point_list[pos] = (uint32_t)(b * DIRECT_BLOCK + gl);
+                inst_pos[pos] = aw.x + (tz * (aw.y >> 16) + ty) * (aw.y & 0xffffu) + tx;
+                ++pos;
             }
         }
-        __syncthreads();
-        for (int t = tid; t < T; t += DIRECT_BLOCK) s_base[t] += s_tot[t];
-        __syncthreads();
     }
 }
 
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
-                       const DirectBin& db, const uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
+                       const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
                        int gy) {
-    const size_t smem = (size_t)db.num_tiles * (4 + 2 + 16);
+    const size_t smem = (size_t)db.num_tiles * 36;
     if (smem > 40 * 1024)
         R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DIRECT_MAX_TILES * 22));
+                                         DIRECT_MAX_TILES * 36));
     direct_fill_kernel<<<db.nb + 1, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
                                                               bv.point_list, bv.inst_pos, bv.capacity, gx, gy);
     R2X_CUDA_OK(cudaGetLastError());

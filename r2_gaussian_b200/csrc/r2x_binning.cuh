@@ -77,16 +77,15 @@ BinningView binning_view(void* buf, long long R);
 // No instance list is materialised and nothing is sorted.  The preprocess CTA b (256 consecutive
 // Gaussians) histograms its own instances per tile (`block_tile_histogram`, shared memory) into row b of
 // `table`; `direct_scan` turns every tile's column into exclusive prefixes over the CTAs (= where CTA b's
-// instances of tile t start inside the tile's list), derives the tile ranges, the CTA instance bases and
-// the work plan; `direct_fill` regenerates each CTA's instances in the reference's emission order and
-// writes the Gaussian ids straight to their final, stable positions.  4 kernels per forward in total.
+// instances of tile t start inside the tile's list) and publishes R; `direct_fill` derives the tile ranges
+// and the work plan and writes each CTA's Gaussian ids straight to their final, stable positions (ascending
+// Gaussian id inside a tile).  4 kernels per forward in total.
 constexpr int DIRECT_MAX_TILES = 4096;
 constexpr int DIRECT_BLOCK = 256;       // Gaussians per preprocess CTA (== its thread count)
 struct DirectBin {
-    uint32_t* table;        // [T][nb]
+    uint32_t* table;        // [nb][T]  row b = CTA b's per-tile counts -> exclusive prefix down each column
     uint32_t* tile_count;   // [T]
-    uint32_t* block_total;  // [nb]  instances of CTA b  -> exclusive base after direct_scan
-    uint32_t* done;         // [2]   CTA arrival counter of direct_scan
+    uint32_t* block_total;  // [nb]  instances of CTA b
     int num_tiles, nb;
 };
 size_t directbin_bytes(int P, int num_tiles);
@@ -116,7 +115,7 @@ __device__ __forceinline__ void block_tile_histogram(uint32_t* hist_s, const Dir
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((tid & 31) == 0) s_wsum[tid >> 5] = v;
     __syncthreads();
-    for (int t = tid; t < db.num_tiles; t += DIRECT_BLOCK) db.table[(size_t)t * db.nb + blockIdx.x] = hist_s[t];
+    for (int t = tid; t < db.num_tiles; t += DIRECT_BLOCK) db.table[(size_t)blockIdx.x * db.num_tiles + t] = hist_s[t];
     if (tid == 0) {
         uint32_t tot = 0;
 #pragma unroll
@@ -125,10 +124,10 @@ __device__ __forceinline__ void block_tile_histogram(uint32_t* hist_s, const Dir
     }
 }
 
-int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint2* ranges, const TilePlan& plan, uint32_t* status,
-                       long long capacity, uint32_t* status_out);
+int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, long long capacity,
+                       uint32_t* status_out);
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
-                       const DirectBin& db, const uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
+                       const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
                        int gy);
 
 // Exclusive->inclusive scan of tiles_touched[P] into offsets[P]; total (R) is written to *d_total
