@@ -38,7 +38,7 @@ BinningView binning_view(void* buf, long long R) {
 // ------------------------------------------------------------------------------------------------
 size_t plan_bytes(int num_tiles) {
     size_t t = (size_t)num_tiles;
-    return align_up((t + 1) * sizeof(uint32_t), 256) + align_up(t * sizeof(uint32_t), 256) + 512;
+    return align_up((t + 1) * sizeof(uint32_t), 256) + align_up(t * PLAN_DONE_SLOTS * sizeof(uint32_t), 256) + 512;
 }
 
 TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
@@ -46,7 +46,7 @@ TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
     size_t t = (size_t)num_tiles;
     char* p = (char*)align_up((size_t)buf, 256);
     pl.extra_off = (uint32_t*)p; p += align_up((t + 1) * sizeof(uint32_t), 256);
-    pl.tile_done = (uint32_t*)p; p += align_up(t * sizeof(uint32_t), 256);
+    pl.tile_done = (uint32_t*)p; p += align_up(t * PLAN_DONE_SLOTS * sizeof(uint32_t), 256);
     pl.counter = (uint32_t*)p;
     pl.extra_item = bv.extra_item;
     pl.partial = bv.partial;
@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
             const uint2 r = ranges[t];
             const uint32_t n = r.y - r.x;
             a = n ? (n - 1) / PLAN_CHUNK : 0u;  // extra chunks beyond the first
-            pl.tile_done[t] = 0;
+#pragma unroll
+            for (int k = 0; k < PLAN_DONE_SLOTS; ++k) pl.tile_done[(size_t)t * PLAN_DONE_SLOTS + k] = 0;
         }
         uint32_t ia = a;
 #pragma unroll
@@ -589,8 +590,8 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
         for (int i = tid; i < T; i += DIRECT_BLOCK) {
             const uint32_t ex = s_ex[i];
             ranges[i] = overflow ? make_uint2(0u, 0u) : make_uint2(ex, ex + tc[i]);
-            pl.tile_done[i] = 0;
         }
+        for (int i = tid; i < T * PLAN_DONE_SLOTS; i += DIRECT_BLOCK) pl.tile_done[i] = 0;
         __syncthreads();
         const uint32_t E = cta_exclusive_scan(
             T, [&](int i) { const uint32_t n = overflow ? 0u : tc[i]; return n ? (n - 1) / PLAN_CHUNK : 0u; },

@@ -44,9 +44,10 @@ constexpr int SORT_MAX_BLOCKS = 296;                   // 2 CTAs per SM on 148 S
 // write the zeros); items [T, T+E) are the extra chunks, looked up in `extra_item`.  A tile with several
 // chunks combines its partial sums in chunk order (the last-arriving CTA does it) => deterministic.
 constexpr int PLAN_CHUNK = 256;
+constexpr int PLAN_DONE_SLOTS = 8;   // arrival counters per tile (one per warp of the raster render CTA)
 struct TilePlan {
     uint32_t* extra_off;  // [T+1] exclusive scan of (chunks_t - 1); [T] = E
-    uint32_t* tile_done;  // [T]   arrival counters of multi-chunk tiles
+    uint32_t* tile_done;  // [T][PLAN_DONE_SLOTS] arrival counters of multi-chunk tiles
     uint32_t* counter;    // [4]   work-queue heads (0: forward, 1: backward)
     uint2* extra_item;    // [R/PLAN_CHUNK + 1] (tile, chunk >= 1) of extra item j   (binning buffer)
     float* partial;       // [R/PLAN_CHUNK + 1][512] partial sums of extra chunks      (binning buffer)

@@ -164,6 +164,15 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// atomicAdd with release semantics at gpu scope: everything this thread (and, through a preceding warp/CTA
+// barrier, its peers) wrote before is visible to whoever observes the incremented value.  Cheaper than
+// __threadfence() + atomicAdd, and it does not invalidate the SM's L1.
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
