@@ -147,6 +147,48 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
                      float* conic_opacity, uint32_t* tiles_touched, uint32_t* point_offsets, uint64_t* keys,
                      uint32_t* point_list, uint32_t* ranges);
 
+/* ---- point-cloud initialisation helper ------------------------------------------------------ */
+/* Replaces `simple_knn._C.distCUDA2` (imported at r2_gaussian/gaussian/gaussian_model.py:21, called at
+ * :144-150; upstream gitlab.inria.fr/bkerbl/simple-knn is an un-vendored submodule of the reference):
+ * mean_dist2[i] = mean of the squared distances from points[i] to its 3 nearest OTHER points (exact;
+ * FLT_MAX placeholders -> inf when fewer than 3 other points exist).  points[P,3] and mean_dist2[P] are
+ * device pointers; scratch needs r2x_knn_scratch_bytes(P) bytes.  Asynchronous on `stream`. */
+size_t r2x_knn_scratch_bytes(int P);
+int r2x_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, void* scratch,
+                        size_t scratch_bytes);
+
+/* ---- training-step helpers around the hot path ---------------------------- */
+/* loss = w_l1 * mean|image - target| + w_dssim * (1 - mean SSIM(image, target)) for one single-channel H x W
+ * image: the reference's `l1_loss` + `ssim` (r2_gaussian/utils/loss_utils.py:37-104: 11-tap Gaussian window,
+ * sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2) as combined in train.py:118-127.
+ * loss_out[3] (device) = {mean|x-y|, mean SSIM, loss}; grad_out[H*W] (device, may be NULL) = d loss / d image.
+ * Deterministic.  scratch: r2x_image_loss_scratch_bytes(H, W). */
+size_t r2x_image_loss_scratch_bytes(int H, int W);
+int r2x_image_loss(void* stream, int H, int W, const float* image, const float* target, float w_l1,
+                   float w_dssim, float* loss_out, float* grad_out, void* scratch, size_t scratch_bytes);
+
+/* 3-D total variation of vol[nx][ny][nz] (`tv_3d_loss`, loss_utils.py:19-34): sum of absolute forward
+ * differences along the three axes, divided by their number when reduction_mean != 0.  loss_out[1] (device),
+ * grad_out[nx*ny*nz] (device, may be NULL).  scratch: r2x_tv3d_scratch_bytes(nx, ny, nz). */
+size_t r2x_tv3d_scratch_bytes(int nx, int ny, int nz);
+int r2x_tv3d_loss(void* stream, int nx, int ny, int nz, const float* vol, int reduction_mean, float* loss_out,
+                  float* grad_out, void* scratch, size_t scratch_bytes);
+
+/* One Adam step over several parameter tensors in a single launch (torch.optim.Adam as configured at
+ * r2_gaussian/gaussian/gaussian_model.py:216: amsgrad off, no weight decay; the four groups xyz / density /
+ * scaling / rotation each carry their own learning rate).  `step` counts from 1 (bias correction). */
+#define R2X_ADAM_MAX_GROUPS 8
+typedef struct r2x_adam_group {
+    float* param;        /* [numel] updated in place          */
+    const float* grad;   /* [numel]                           */
+    float* exp_avg;      /* [numel] first moment, in place    */
+    float* exp_avg_sq;   /* [numel] second moment, in place   */
+    long long numel;
+    float lr;
+} r2x_adam_group;
+int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
+                  long long step);
+
 #ifdef __cplusplus
 }
 #endif

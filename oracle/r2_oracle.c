@@ -28,6 +28,7 @@
  *  VOX = .../cuda_voxelizer).
  */
 #define _GNU_SOURCE
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -886,6 +887,32 @@ void orc_mark_visible(int P, const float* means, const float* view, const float*
     for (int i = 0; i < P; ++i) {
         const float* p = means + 3 * i;
         present[i] = xform_row(view, 2, p[0], p[1], p[2]) > 0.2f;
+    }
+}
+
+/* simple_knn._C.distCUDA2 (called at r2_gaussian/gaussian/gaussian_model.py:144-150).  The upstream extension
+ * (gitlab.inria.fr/bkerbl/simple-knn) is an un-vendored submodule of the reference, so this restates its
+ * published result -- for every point the mean of the three smallest squared distances to OTHER points, kept
+ * in ascending order from FLT_MAX placeholders (updateKBest<3>) -- by brute force.  PARITY UNPINNED against
+ * the upstream binary (absent); pinned against an independent float64 k-d tree in tests/test_oracle_cpu.py. */
+void orc_knn3_mean_dist2(int P, const float* pts, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; ++i) {
+        float b0 = FLT_MAX, b1 = FLT_MAX, b2 = FLT_MAX;
+        const float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+        for (int j = 0; j < P; ++j) {
+            if (j == i) continue;
+            const float dx = x - pts[3 * (size_t)j], dy = y - pts[3 * (size_t)j + 1], dz = z - pts[3 * (size_t)j + 2];
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d < b2) {
+                if (d < b1) {
+                    b2 = b1;
+                    if (d < b0) { b1 = b0; b0 = d; }
+                    else b1 = d;
+                } else b2 = d;
+            }
+        }
+        out[i] = ((b0 + b1) + b2) / 3.0f;
     }
 }
 

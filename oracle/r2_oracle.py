@@ -209,3 +209,12 @@ def mark_visible(means, view, proj):
     lib().orc_mark_visible(C.c_int(means.shape[0]), _p(means, _fp), _p(_c(view, _f).reshape(16), _fp),
                            _p(_c(proj, _f).reshape(16), _fp), present.ctypes.data_as(C.POINTER(C.c_ubyte)))
     return present.astype(bool)
+
+
+def knn3_mean_dist2(points):
+    """Brute-force restatement of simple_knn._C.distCUDA2 (see orc_knn3_mean_dist2)."""
+    pts = _c(points, _f).reshape(-1, 3)
+    out = np.zeros(pts.shape[0], _f)
+    with np.errstate(over="ignore"):
+        lib().orc_knn3_mean_dist2(C.c_int(pts.shape[0]), _p(pts, _fp), _p(out, _fp))
+    return out

@@ -45,7 +45,20 @@ PROTOTYPES = {
     "r2x_voxel_backward": (_i, [_vp, _i, _ll, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _f, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "r2x_voxel_export": (_i, [_vp, _i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "r2x_knn_scratch_bytes": (_sz, [_i]),
+    "r2x_knn3_mean_dist2": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "r2x_image_loss_scratch_bytes": (_sz, [_i, _i]),
+    "r2x_image_loss": (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _sz]),
+    "r2x_tv3d_scratch_bytes": (_sz, [_i, _i, _i]),
+    "r2x_tv3d_loss": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz]),
+    "r2x_adam_step": (_i, [_vp, _i, _vp, C.c_double, C.c_double, C.c_double, _ll]),
 }
+
+
+class AdamGroup(C.Structure):
+    """Mirror of `r2x_adam_group` (include/r2x.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_longlong), ("lr", C.c_float)]
 
 _lock = threading.Lock()
 _lib = None

@@ -10,6 +10,8 @@
 #include "r2x_voxel.cuh"
 
 namespace r2x {
+int launch_adam(cudaStream_t st, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
+                long long step);
 
 static thread_local std::string g_err;
 
@@ -564,6 +566,36 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+size_t r2x_knn_scratch_bytes(int P) { return r2x::knn_scratch_bytes(P); }
+
+int r2x_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, void* scratch,
+                        size_t scratch_bytes) {
+    if (P < 0) return fail_msg(R2X_ERR_INVALID, "r2x_knn3_mean_dist2: bad P");
+    return r2x::launch_knn3((cudaStream_t)stream, P, points, mean_dist2, scratch, scratch_bytes);
+}
+
+size_t r2x_image_loss_scratch_bytes(int H, int W) { return r2x::image_loss_scratch_bytes(H, W); }
+
+int r2x_image_loss(void* stream, int H, int W, const float* image, const float* target, float w_l1, float w_dssim,
+                   float* loss_out, float* grad_out, void* scratch, size_t scratch_bytes) {
+    return r2x::launch_image_loss((cudaStream_t)stream, H, W, image, target, w_l1, w_dssim, loss_out, grad_out, scratch,
+                                  scratch_bytes);
+}
+
+size_t r2x_tv3d_scratch_bytes(int nx, int ny, int nz) { return r2x::tv3d_scratch_bytes(nx, ny, nz); }
+
+int r2x_tv3d_loss(void* stream, int nx, int ny, int nz, const float* vol, int reduction_mean, float* loss_out,
+                  float* grad_out, void* scratch, size_t scratch_bytes) {
+    return r2x::launch_tv3d((cudaStream_t)stream, nx, ny, nz, vol, reduction_mean, loss_out, grad_out, scratch,
+                            scratch_bytes);
+}
+
+int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
+                  long long step) {
+    if (ngroups > 0 && !groups) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: null groups");
+    return r2x::launch_adam((cudaStream_t)stream, ngroups, groups, beta1, beta2, eps, step);
 }
 
 }  // extern "C"

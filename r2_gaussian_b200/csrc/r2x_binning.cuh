@@ -147,4 +147,16 @@ int launch_emit(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* ti
 int launch_sort_and_ranges(cudaStream_t st, long long R_launch, int num_tiles, const uint32_t* d_total,
                            const BinningView& bv, uint2* ranges, uint32_t** sorted_keys_out);
 
+// exact 3-NN mean squared distance (r2x_knn.cu)
+size_t knn_scratch_bytes(int P);
+int launch_knn3(cudaStream_t st, int P, const float* points, float* out, void* scratch, size_t scratch_bytes);
+
+// training-step helpers (r2x_train.cu)
+size_t image_loss_scratch_bytes(int H, int W);
+int launch_image_loss(cudaStream_t st, int H, int W, const float* image, const float* target, float w_l1,
+                      float w_dssim, float* loss_out, float* grad_out, void* scratch, size_t scratch_bytes);
+size_t tv3d_scratch_bytes(int nx, int ny, int nz);
+int launch_tv3d(cudaStream_t st, int nx, int ny, int nz, const float* vol, int reduction_mean, float* loss_out,
+                float* grad_out, void* scratch, size_t scratch_bytes);
+
 }  // namespace r2x

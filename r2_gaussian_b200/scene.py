@@ -109,6 +109,19 @@ def make_view(scanner: dict, angle: float) -> View:
                 np.ascontiguousarray(full), campos, mode, angle, fovx, fovy)
 
 
+def camera_from_view(view: View, device="cuda"):
+    """The attributes render() reads from the reference's `Camera` (`r2_gaussian/dataset/cameras.py:20-70`:
+    world_view_transform, full_proj_transform, camera_center, FoVx/FoVy, image size, mode) as device tensors."""
+    import types
+
+    import torch
+    return types.SimpleNamespace(
+        image_height=view.image_height, image_width=view.image_width, FoVx=view.FoVx, FoVy=view.FoVy, mode=view.mode,
+        world_view_transform=torch.tensor(view.viewmatrix, device=device),
+        full_proj_transform=torch.tensor(view.projmatrix, device=device),
+        camera_center=torch.tensor(view.campos, device=device), angle=view.angle)
+
+
 def make_views(scanner: dict, n_views: int = 50) -> list[View]:
     """Angles linspace(0, 2pi, n+1)[:-1] (data_generator/synthetic_dataset/generate_data.py:47-50)."""
     angles = np.linspace(0.0, 2.0 * math.pi, n_views + 1)[:-1]

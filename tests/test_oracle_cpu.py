@@ -164,3 +164,17 @@ def test_golden_vectors():
             util.assert_grads_close(g, {k[2:]: z[k] for k in z.files if k.startswith("g_")},
                                     ["dL_dopacity", "dL_dmean3D", "dL_dscale", "dL_drot"], rtol=5e-4, atol_rel=5e-5,
                                     label=fn + " ")
+
+
+def test_knn_oracle_vs_kdtree():
+    """orc_knn3_mean_dist2 (the restated simple_knn.distCUDA2) against an independent float64 k-d tree."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(11)
+    for pts in (rng.normal(size=(1500, 3)), rng.uniform(-1, 1, size=(800, 3)) * [1, 1, 0.01]):
+        pts = pts.astype(np.float32)
+        got = orc.knn3_mean_dist2(pts)
+        d, _ = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=4)
+        ref = (d[:, 1:] ** 2).mean(1)
+        assert np.allclose(got, ref, rtol=2e-6, atol=1e-12)
+    two = orc.knn3_mean_dist2(np.zeros((2, 3), np.float32))
+    assert np.all(two > 1e37)          # fewer than 3 neighbours: FLT_MAX placeholders, as upstream
