@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--cloud", default="init", choices=["init", "trained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the per-rank partial images are summed (NVLink peer-memory kernel | NCCL)")
     return ap.parse_args()
 
 
@@ -237,7 +239,20 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # N > 1: the exchange step.  Default = one-shot sum over NVLink peer memory (r2x_peer_allreduce_sum: every
+    # rank renders into an IPC-shared partial image, one kernel adds the partials in rank order); --reduce nccl
+    # uses dist.all_reduce instead.
+    reducer = None
+    if world > 1 and args.reduce == "p2p":
+        from r2_gaussian_b200.peer import PeerReducer
+        reducer = PeerReducer(W * H, dev)
+    final = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+
     def step(i):
+        if reducer is not None:
+            fwd(i, out=reducer.partial().view(1, H, W))
+            reducer.reduce(final)
+            return
         out = fwd(i)
         if world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
@@ -251,7 +266,12 @@ def run_ours(args, rank, world, local_rank):
     # side stream and overlaps the render of step i+1 (ring of output buffers)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
+    if world > 1 and reducer is not None:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+    elif world > 1:
         ring = [torch.empty((1, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
         comm = torch.cuda.Stream(device=dev)
         done = [None] * 4
@@ -281,6 +301,8 @@ def run_ours(args, rank, world, local_rank):
         total_ms, warm_ms = float(t[0]), float(t[1])
     # overflow check for the timed region (status of the last forward; capacity is per scene)
     assert eng.check(), "instance capacity overflowed during the timed region"
+    if reducer is not None:
+        assert reducer.ok(), "a peer never arrived in r2x_peer_allreduce_sum"
 
     # ---- roofline of the dominant kernel (rank 0's shard) ----
     fwd(0)
@@ -307,11 +329,13 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"{args.gaussians} Gaussians ({args.cloud}-like, seed 0), {W}x{H} cone-beam "
                                f"(DSD 7, DSO 5), {args.views} views cycled; forward projection",
                    "gaussians": args.gaussians, "detector": [H, W], "views": args.views,
-                   "parallelism": f"gaussian-shard x{world}" + (" + NCCL all-reduce of the image" if world > 1 else ""),
+                   "parallelism": f"gaussian-shard x{world}" + ((" + one-shot NVLink peer-memory sum of the image (r2x_peer_allreduce_sum)"
+                                                                   if args.reduce == "p2p" else " + NCCL all-reduce of the image") if world > 1 else ""),
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "num_rendered_mean": R_mean * 1.0, "api": "r2x_raster_forward_async (C ABI, no host sync)"},
         "value_warm_l2_back_to_back": args.steps / (warm_ms * 1e-3),  # N > 1: all-reduce overlapped with the next render
-        "gpu_launches": args.steps * 4,  # preprocess(+tile histogram), direct_scan, direct_fill, render
+        # preprocess(+tile histogram), direct_scan, direct_fill, render (+ the peer-memory sum when N > 1)
+        "gpu_launches": args.steps * (5 if (world > 1 and args.reduce == "p2p") else 4),
         "roofline": roofline,
         "clocks": sampler.summary(),
     }
@@ -335,7 +359,10 @@ def run_ours(args, rank, world, local_rank):
                 campos=hc.to(dev, non_blocking=True), prefiltered=False, mode=v.mode, debug=False)
             with torch.no_grad():
                 img, _radii = GaussianRasterizer(settings)(means3D=m, means2D=None, opacities=d, scales=s, rotations=r)
-            if world > 1:
+            if reducer is not None:
+                reducer.partial().view_as(img).copy_(img)
+                img = reducer.reduce(final)
+            elif world > 1:
                 dist.all_reduce(img, op=dist.ReduceOp.SUM)
             h_out.copy_(img, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()

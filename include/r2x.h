@@ -189,6 +189,24 @@ typedef struct r2x_adam_group {
 int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
                   long long step);
 
+/* ---- multi-GPU exchange step: one-shot sum over NVLink peer memory ------------------------------ */
+/* The Gaussian-sharded projector (one process per GPU, every rank renders its index shard) needs ONE exchange per
+ * projection: the sum of the per-rank partial detector images (BASELINE north_star; the reference itself is
+ * single-GPU).  These entry points replace the NCCL all-reduce for that step: buffers are cudaMalloc'ed
+ * (r2x_peer_alloc), shared between the processes of one node as CUDA IPC handles (64 bytes, r2x_ipc_export /
+ * r2x_ipc_open), and r2x_peer_allreduce_sum signals, waits and adds the `world` partial buffers in rank order
+ * (bitwise identical result on every rank).  bufs[p] / flags[p]: rank p's partial buffer (n floats) and flag
+ * array (R2X_MAX_PEERS uint32, zero-initialised) as mapped in THIS process; `epoch` increases by one per call;
+ * callers double-buffer the partial buffers by epoch parity.  status_dev[0] is set to 1 if a peer never arrived. */
+#define R2X_MAX_PEERS 16
+int r2x_peer_alloc(size_t bytes, void** dev_ptr);
+int r2x_peer_free(void* dev_ptr);
+int r2x_ipc_export(void* dev_ptr, unsigned char* handle64);
+int r2x_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int r2x_ipc_close(void* dev_ptr);
+int r2x_peer_allreduce_sum(void* stream, int world, int rank, const float* const* bufs, uint32_t* const* flags,
+                           uint32_t epoch, float* out, long long n, uint32_t* status_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,12 @@ PROTOTYPES = {
     "r2x_tv3d_scratch_bytes": (_sz, [_i, _i, _i]),
     "r2x_tv3d_loss": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz]),
     "r2x_adam_step": (_i, [_vp, _i, _vp, C.c_double, C.c_double, C.c_double, _ll]),
+    "r2x_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "r2x_peer_free": (_i, [_vp]),
+    "r2x_ipc_export": (_i, [_vp, _vp]),
+    "r2x_ipc_open": (_i, [_vp, C.POINTER(_vp)]),
+    "r2x_ipc_close": (_i, [_vp]),
+    "r2x_peer_allreduce_sum": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp]),
 }
 
 
