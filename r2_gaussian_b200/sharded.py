@@ -6,9 +6,10 @@ kernels and one all-reduce(sum) makes the full image available on every rank -- 
 backward pass needs: the loss and dL/dimage are then replicated by construction and each rank
 back-propagates into its own shard with no further communication.
 
-The exchange step is `torch.distributed.all_reduce` (NCCL over NVLink on GPUs; gloo in the CPU tests).
-The per-rank renderer is injectable so the host logic (partition, reduction, bookkeeping) is testable
-without a GPU.
+The exchange step is `torch.distributed.all_reduce` (NCCL over NVLink on GPUs; gloo in the CPU tests) or,
+after `enable_peer_exchange()`, the one-kernel sum over NVLink peer memory of `r2_gaussian_b200.peer`
+(rank-ordered, bitwise identical on all ranks).  The per-rank renderer is injectable so the host logic
+(partition, reduction, bookkeeping) is testable without a GPU.
 """
 from __future__ import annotations
 
@@ -29,11 +30,38 @@ def world_info() -> tuple[int, int]:
     return 0, 1
 
 
+_PEER = {"on": False, "reducers": {}}
+
+
+def enable_peer_exchange(on: bool = True):
+    """Route all_reduce_sum() of CUDA float32 tensors through PeerReducer (single node, one process per GPU).
+    Reducers are created on first use per tensor size -- collectively, so every rank must reduce the same sizes in
+    the same order (true for render()/query(), whose outputs are replicated shapes)."""
+    _PEER["on"] = bool(on)
+    if not on:
+        for r in _PEER["reducers"].values():
+            r.close()
+        _PEER["reducers"].clear()
+
+
+def _peer_reducer(x, group):
+    key = (x.numel(), x.device.index, id(group))
+    red = _PEER["reducers"].get(key)
+    if red is None:
+        from .peer import PeerReducer
+        red = _PEER["reducers"][key] = PeerReducer(x.numel(), x.device, group)
+    return red
+
+
 class _AllReduceSum(torch.autograd.Function):
     """y = sum over ranks of x.  Backward: every rank already holds the full dL/dy, and dy/dx_r = I."""
 
     @staticmethod
     def forward(ctx, x, group):
+        if _PEER["on"] and x.is_cuda and x.dtype == torch.float32:
+            red = _peer_reducer(x, group)
+            red.partial().view_as(x).copy_(x)
+            return red.reduce(torch.empty_like(x, memory_format=torch.contiguous_format))
         y = x.contiguous().clone()
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
         return y

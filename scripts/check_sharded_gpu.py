@@ -8,11 +8,13 @@ from types import SimpleNamespace
 import util
 from r2_gaussian_b200 import scene
 from r2_gaussian_b200.render_query import render, query
-from r2_gaussian_b200.sharded import shard_bounds
+from r2_gaussian_b200.sharded import shard_bounds, enable_peer_exchange
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+if "--p2p" in sys.argv:
+    enable_peer_exchange(True)     # NVLink peer-memory sum instead of NCCL for the image / volume exchange
 cloud, view = util.case("cone_trained_mid")
 dev = torch.device("cuda", lr)
 def model(c):
@@ -43,5 +45,6 @@ e_vol = ((vol - vol_full).abs().max() / vol_full.abs().max()).item()
 e_g = max(((t[k].grad - full[k].grad[lo:hi]).abs().max() / (full[k].grad.abs().max() + 1e-30)).item() for k in t)
 ok = e_img <= 1e-5 and e_vol <= 1e-5 and e_g <= 1e-5
 print(f"rank {rank}/{world}: image err {e_img:.2e}, volume err {e_vol:.2e}, shard-gradient err {e_g:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+enable_peer_exchange(False)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
