@@ -312,6 +312,14 @@ class GaussianModel:
         return grads
 
     def add_densification_stats(self, viewspace_point_tensor, update_filter):
-        self.xyz_gradient_accum[update_filter] += torch.norm(viewspace_point_tensor.grad[update_filter, :2], dim=-1,
-                                                             keepdim=True)
-        self.denom[update_filter] += 1
+        """Accumulate |dL/dmean2D| of the visible Gaussians (`:552-556`).  Written without boolean-mask indexing
+        (which costs a host round trip per call): invisible rows add exactly 0."""
+        seen = update_filter.unsqueeze(-1)
+        norm = torch.norm(viewspace_point_tensor.grad[:, :2], dim=-1, keepdim=True)
+        self.xyz_gradient_accum += torch.where(seen, norm, torch.zeros_like(norm))
+        self.denom += seen.to(self.denom.dtype)
+
+    def update_max_radii(self, radii, visibility_filter):
+        """max_radii2D[vis] = max(max_radii2D[vis], radii[vis]) (train.py:150-152) without a host round trip."""
+        r = radii.to(self.max_radii2D.dtype)
+        self.max_radii2D = torch.where(visibility_filter, torch.maximum(self.max_radii2D, r), self.max_radii2D)

@@ -122,7 +122,7 @@ def main():
         loss.backward()
         with torch.no_grad():
             vis = pkg["visibility_filter"]
-            gm.max_radii2D[vis] = torch.max(gm.max_radii2D[vis], pkg["radii"][vis].float())
+            gm.update_max_radii(pkg["radii"], vis)
             gm.add_densification_stats(pkg["viewspace_points"], vis)
         gm.optimizer.step()
         gm.optimizer.zero_grad(set_to_none=True)

@@ -346,3 +346,25 @@ def test_short_training_run_reduces_the_loss():
         start.optimizer.zero_grad(set_to_none=True)
         history.append(float(loss["total"]))
     assert history[-1] < 0.7 * history[0], history[::8]
+
+
+def test_densification_stats_without_mask_indexing():
+    gm, _, _ = _make_model(n=300, seed=9)
+    vsp = torch.zeros(300, 3, device="cuda", requires_grad=True)
+    vsp.grad = torch.randn(300, 3, device="cuda")
+    vsp.grad[5] = float("nan")                         # an invisible row may hold anything
+    vis = torch.rand(300, device="cuda") > 0.4
+    vis[5] = False
+    acc0, den0 = gm.xyz_gradient_accum.clone(), gm.denom.clone()
+    gm.add_densification_stats(vsp, vis)
+    want = acc0.clone()
+    want[vis] += torch.norm(vsp.grad[vis, :2], dim=-1, keepdim=True)      # the reference's statement (:552-556)
+    den = den0.clone()
+    den[vis] += 1
+    assert torch.equal(gm.xyz_gradient_accum, want) and torch.equal(gm.denom, den)
+    radii = torch.randint(0, 50, (300,), device="cuda", dtype=torch.int32)
+    before = gm.max_radii2D.clone()
+    gm.update_max_radii(radii, vis)
+    ref = before.clone()
+    ref[vis] = torch.max(ref[vis], radii[vis].float())
+    assert torch.equal(gm.max_radii2D, ref)
