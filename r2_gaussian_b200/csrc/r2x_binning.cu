@@ -440,7 +440,7 @@ size_t directbin_bytes(int P, int num_tiles) {
     const size_t nb = (size_t)((P > 0 ? P : 1) + DIRECT_BLOCK - 1) / DIRECT_BLOCK;
     const size_t t = (size_t)num_tiles;
     return align_up(t * nb * sizeof(uint32_t), 256) + align_up(t * sizeof(uint32_t), 256) +
-           align_up(nb * sizeof(uint32_t), 256) + 512;
+           2 * align_up(nb * sizeof(uint32_t), 256) + 512;
 }
 
 DirectBin directbin_view(void* buf, int P, int num_tiles) {
@@ -451,6 +451,7 @@ DirectBin directbin_view(void* buf, int P, int num_tiles) {
     db.table = (uint32_t*)p; p += align_up(t * nb * sizeof(uint32_t), 256);
     db.tile_count = (uint32_t*)p; p += align_up(t * sizeof(uint32_t), 256);
     db.block_total = (uint32_t*)p; p += align_up(nb * sizeof(uint32_t), 256);
+    db.block_base = (uint32_t*)p; p += align_up(nb * sizeof(uint32_t), 256);
     db.num_tiles = num_tiles;
     db.nb = (int)nb;
     return db;
@@ -484,6 +485,46 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(int n, Load load, Store s
         __syncthreads();
     }
     return *s_carry;
+}
+
+// One-pass variant for n <= 16 * 256: thread t owns the K = ceil(n/256) consecutive elements [tK, tK+K), so the
+// whole scan costs one round of loads, one warp scan and two barriers (the strip-mined version above pays a
+// dependent global load + three barriers per 256 elements, which dominated direct_fill's prologue).
+template <typename V, typename Load, typename Store>
+__device__ __forceinline__ V cta_exclusive_scan_1pass(int n, Load load, Store store, V* s_w) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = (n + 255) >> 8;
+    V val[16], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid * K + k;
+        val[k] = (k < K && i < n) ? load(i) : V(0);
+        sum += val[k];
+    }
+    V ia = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const V t = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += t;
+    }
+    __syncthreads();            // s_w may still be read by a previous scan
+    if (lane == 31) s_w[warp] = ia;
+    __syncthreads();
+    V wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const V x = s_w[w];
+        if (w < warp) wpre += x;
+        total += x;
+    }
+    V ex = wpre + ia - sum;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid * K + k;
+        if (k < K && i < n) store(i, ex, val[k], total);
+        ex += val[k];
+    }
+    return total;
 }
 
 // Column scan of table[nb][T]: CTA = 32 tiles x 32 row segments (1024 threads); every thread sums its rows of
@@ -535,15 +576,31 @@ __global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_
         }
     }
     if (blockIdx.x == 0) {
-        uint32_t v = 0;
-        for (int i = threadIdx.x; i < nb; i += 1024) v += db.block_total[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[seg] = v;
+        // instance base of every preprocess CTA (exclusive prefix of the CTA totals), R and the overflow flag
+        __shared__ uint32_t s_carry;
+        if (threadIdx.x == 0) s_carry = 0;
         __syncthreads();
+        for (int base = 0; base < nb; base += 1024) {
+            const int i = base + threadIdx.x;
+            const uint32_t a = i < nb ? db.block_total[i] : 0u;
+            uint32_t ia = a;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, ia, o);
+                if (lane >= o) ia += x;
+            }
+            if (lane == 31) s_red[seg] = ia;
+            __syncthreads();
+            uint32_t wpre = 0;
+            for (int w = 0; w < seg; ++w) wpre += s_red[w];
+            const uint32_t ex = s_carry + wpre + ia - a;
+            if (i < nb) db.block_base[i] = ex;
+            __syncthreads();
+            if (threadIdx.x == 1023) s_carry = ex + a;
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
-            uint32_t R = 0;
-            for (int w = 0; w < 32; ++w) R += s_red[w];
+            const uint32_t R = s_carry;
             const uint32_t ov = ((long long)R > capacity) ? 1u : 0u;
             status[0] = R;
             status[1] = ov;
@@ -564,8 +621,8 @@ int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, l
 // set bits in ascending order = ascending Gaussian id, which is the stable order, and writes the ids to
 // range[t].x + prefix[b][t] + k.  No search, no division per instance, no warp match.  Every CTA derives the
 // tile ranges and its instance base itself (exclusive scans of tile_count / block_total: small and L2-hot),
-// so nothing serial sits between the column scan and this kernel.  The extra CTA (b == nb) publishes the
-// ranges and the work plan for the render.  Dynamic shared memory: mask[8][T] u32 | base[T] u32.
+// so nothing serial sits between the column scan and this kernel; the publication of the ranges and of the
+// work plan for the render is spread over the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32.
 __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const uint16_t* __restrict__ cube,
                                                                    const uint32_t* __restrict__ tiles_touched,
                                                                    uint32_t* __restrict__ offsets, DirectBin db,
@@ -574,41 +631,14 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
                                                                    uint32_t* __restrict__ inst_pos, long long capacity,
                                                                    int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_w[8];
-    __shared__ uint32_t s_carry;
+    __shared__ unsigned long long s_w[8];
     const int T = db.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tc = db.tile_count;
-    if ((int)blockIdx.x == db.nb) {   // extra CTA: tile ranges + work plan
-        uint32_t* s_ex = reinterpret_cast<uint32_t*>(smem_raw);
-        const uint32_t R = cta_exclusive_scan(
-            T, [&](int i) { return tc[i]; }, [&](int i, uint32_t ex, uint32_t) { s_ex[i] = ex; }, s_w, &s_carry);
-        // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so publish EMPTY
-        // ranges -- the render then produces zeros without touching unwritten list entries -- and the host
-        // sees status[1] = 1 (direct_scan) and re-runs with a larger buffer.
-        const bool overflow = (long long)R > capacity;
-        for (int i = tid; i < T; i += DIRECT_BLOCK) {
-            const uint32_t ex = s_ex[i];
-            ranges[i] = overflow ? make_uint2(0u, 0u) : make_uint2(ex, ex + tc[i]);
-        }
-        for (int i = tid; i < T * PLAN_DONE_SLOTS; i += DIRECT_BLOCK) pl.tile_done[i] = 0;
-        __syncthreads();
-        const uint32_t E = cta_exclusive_scan(
-            T, [&](int i) { const uint32_t n = overflow ? 0u : tc[i]; return n ? (n - 1) / PLAN_CHUNK : 0u; },
-            [&](int i, uint32_t ex, uint32_t ne) {
-                pl.extra_off[i] = ex;
-                for (uint32_t c = 0; c < ne; ++c)
-                    if ((long long)(ex + c) < pl.max_extra) pl.extra_item[ex + c] = make_uint2((uint32_t)i, c + 1);
-            },
-            s_w, &s_carry);
-        if (tid == 0) pl.extra_off[T] = E;
-        if (tid < 4) pl.counter[tid] = 0;
-        return;
-    }
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);   // [8][T]
     uint32_t* s_base = s_mask + 8 * (size_t)T;                   // [T]
     __shared__ uint2 s_aw[DIRECT_BLOCK];   // per Gaussian: (slot of its first instance - index of its first tile, w | h << 16)
-    __shared__ uint32_t s_w8[8], s_bb[8];
+    __shared__ uint32_t s_w8[8];
 
     const int b = blockIdx.x;
     const int g = b * DIRECT_BLOCK + tid;
@@ -619,11 +649,7 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
         const uint32_t* c = reinterpret_cast<const uint32_t*>(cube + 6 * (size_t)g);
         c01 = c[0]; c23 = c[1]; c45 = c[2];
     }
-    // instance base of this CTA = sum of the totals of the CTAs before it
-    uint32_t bsum = 0;
-    for (int i = tid; i < b; i += DIRECT_BLOCK) bsum += db.block_total[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    const uint32_t bbase = db.block_base[b];   // instance base of this CTA (direct_scan)
     // CTA-exclusive scan of n
     uint32_t ia = n;
 #pragma unroll
@@ -632,17 +658,47 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
         if (lane >= o) ia += x;
     }
     if (lane == 31) s_w8[warp] = ia;
-    if (lane == 0) s_bb[warp] = bsum;
     // where this CTA's run starts inside every tile list
     const uint32_t* row = db.table + (size_t)b * T;
-    const uint32_t R = cta_exclusive_scan(
-        T, [&](int i) { return tc[i]; }, [&](int i, uint32_t ex, uint32_t) { s_base[i] = ex + row[i]; }, s_w, &s_carry);
-    uint32_t wpre = 0, bbase = 0;
+    // One pass over the tile counts gives, per tile, the start of its list (low word) and of its extra work items
+    // (high word: chunks beyond the first).  Besides its own bases every CTA publishes a slice of the tile ranges
+    // and of the work plan for the render -- thread tid of CTA b owns the K tiles [tid K, tid K + K) iff
+    // tid == b (mod npub) -- so no serial tail is left.
+    // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so EMPTY ranges are
+    // published -- the render then produces zeros without touching unwritten list entries -- and the host sees
+    // status[1] = 1 (direct_scan) and re-runs with a larger buffer.
+    const int npub = db.nb < DIRECT_BLOCK ? db.nb : DIRECT_BLOCK;
+    const bool pub = (b < npub) && (tid % npub == b);
+    const unsigned long long tot = cta_exclusive_scan_1pass<unsigned long long>(
+        T,
+        [&](int i) {
+            const uint32_t c = tc[i];
+            return ((unsigned long long)(c ? (c - 1) / PLAN_CHUNK : 0u) << 32) | c;
+        },
+        [&](int i, unsigned long long ex64, unsigned long long v64, unsigned long long total) {
+            const uint32_t ex = (uint32_t)ex64, cnt = (uint32_t)v64;
+            s_base[i] = ex + row[i];
+            if (pub) {
+                const bool ov = (long long)(uint32_t)total > capacity;
+                const uint32_t eo = ov ? 0u : (uint32_t)(ex64 >> 32), ne = ov ? 0u : (uint32_t)(v64 >> 32);
+                ranges[i] = ov ? make_uint2(0u, 0u) : make_uint2(ex, ex + cnt);
+                pl.extra_off[i] = eo;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w < warp) wpre += s_w8[w];
-        bbase += s_bb[w];
+                for (int k = 0; k < PLAN_DONE_SLOTS; ++k) pl.tile_done[(size_t)i * PLAN_DONE_SLOTS + k] = 0;
+                for (uint32_t c = 0; c < ne; ++c)
+                    if ((long long)(eo + c) < pl.max_extra) pl.extra_item[eo + c] = make_uint2((uint32_t)i, c + 1);
+            }
+        },
+        s_w);
+    const uint32_t R = (uint32_t)tot;
+    if (b == 0 && tid == 0) {
+        pl.extra_off[T] = ((long long)R > capacity) ? 0u : (uint32_t)(tot >> 32);
+        pl.counter[0] = pl.counter[1] = pl.counter[2] = pl.counter[3] = 0;
     }
+    uint32_t wpre = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (w < warp) wpre += s_w8[w];
     const uint32_t lex = wpre + ia - n;
     if (g < P) offsets[g] = bbase + lex + n;     // inclusive scan, same meaning as the reference's point_offsets
     if ((long long)R > capacity) return;         // overflow: nothing may be written (uniform across the grid)
@@ -692,7 +748,7 @@ int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint3
     if (smem > 40 * 1024)
         R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          DIRECT_MAX_TILES * 36));
-    direct_fill_kernel<<<db.nb + 1, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
+    direct_fill_kernel<<<db.nb, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
                                                               bv.point_list, bv.inst_pos, bv.capacity, gx, gy);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -87,6 +87,7 @@ struct DirectBin {
     uint32_t* table;        // [nb][T]  row b = CTA b's per-tile counts -> exclusive prefix down each column
     uint32_t* tile_count;   // [T]
     uint32_t* block_total;  // [nb]  instances of CTA b
+    uint32_t* block_base;   // [nb]  exclusive prefix of block_total (direct_scan)
     int num_tiles, nb;
 };
 size_t directbin_bytes(int P, int num_tiles);
