@@ -142,3 +142,81 @@ class VoxelEngine:
             if self.check():
                 break
         return self.num_rendered()
+
+
+class HostProjector:
+    """Projection service over HOST buffers: pinned host parameters in, pinned host image out.
+
+    `project()` is the strict call (upload -> 4 kernels -> download -> wait).  `submit()` / `wait()` pipeline
+    consecutive projections: the upload of request i+1 and the download of image i-1 run on their own streams
+    while request i computes (device inputs / outputs are ring-buffered `depth` deep; one RasterEngine, so the
+    kernels themselves stay in order).  The instance-capacity status of every request travels back with its
+    image; `wait()` re-runs a request synchronously with a larger workspace if it had overflowed.
+    """
+
+    def __init__(self, P: int, W: int, H: int, device="cuda", depth: int = 3, capacity: int | None = None):
+        self.engine = RasterEngine(P, W, H, device, capacity)
+        self.device = self.engine.device
+        self.depth = int(depth)
+        dev, f32 = self.device, torch.float32
+        with torch.cuda.device(dev):
+            mk = lambda *s: [torch.empty(s, dtype=f32, device=dev) for _ in range(self.depth)]
+            self.d_means, self.d_dens, self.d_scales, self.d_rots = mk(P, 3), mk(P, 1), mk(P, 3), mk(P, 4)
+            self.d_view, self.d_proj, self.d_campos = mk(4, 4), mk(4, 4), mk(3)
+            self.d_out = mk(1, H, W)
+            self.d_status = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(self.depth)]
+            self.h_status = [torch.zeros(2, dtype=torch.int32).pin_memory() for _ in range(self.depth)]
+            self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self.s_compute = torch.cuda.Stream(device=dev)
+            ev = lambda: [torch.cuda.Event() for _ in range(self.depth)]
+            self.e_in, self.e_comp, self.e_out = ev(), ev(), ev()
+        self._n = 0
+        self._pending = {}
+
+    def submit(self, h_means, h_dens, h_scales, h_rots, h_view, h_proj, h_campos, tanfovx, tanfovy, mode, h_out):
+        """Enqueue one projection; returns a ticket for wait().  All host tensors should be pinned."""
+        k = self._n % self.depth
+        ticket = self._n
+        self._n += 1
+        if ticket - self.depth in self._pending:      # the ring slot is still owned by an unfinished request
+            self.wait(ticket - self.depth)
+        with torch.cuda.stream(self.s_in):
+            if ticket >= self.depth:
+                self.s_in.wait_event(self.e_comp[k])      # slot inputs free once the previous user computed
+            for d, h in ((self.d_means, h_means), (self.d_dens, h_dens), (self.d_scales, h_scales), (self.d_rots, h_rots),
+                         (self.d_view, h_view), (self.d_proj, h_proj), (self.d_campos, h_campos)):
+                d[k].copy_(h.view_as(d[k]), non_blocking=True)
+            self.e_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_compute):
+            self.s_compute.wait_event(self.e_in[k])
+            if ticket >= self.depth:
+                self.s_compute.wait_event(self.e_out[k])  # slot output free once its previous image went home
+            self.engine.forward(self.d_means[k], self.d_dens[k], self.d_scales[k], self.d_rots[k], self.d_view[k],
+                                self.d_proj[k], self.d_campos[k], tanfovx, tanfovy, mode, out=self.d_out[k])
+            self.d_status[k].copy_(self.engine.status, non_blocking=True)
+            self.e_comp[k].record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.e_comp[k])
+            h_out.copy_(self.d_out[k].view_as(h_out), non_blocking=True)
+            self.h_status[k].copy_(self.d_status[k], non_blocking=True)
+            self.e_out[k].record(self.s_out)
+        self._pending[ticket] = (k, (h_means, h_dens, h_scales, h_rots, h_view, h_proj, h_campos, tanfovx, tanfovy, mode,
+                                     h_out))
+        return ticket
+
+    def wait(self, ticket):
+        k, req = self._pending.pop(ticket)
+        self.e_out[k].synchronize()
+        if int(self.h_status[k][1]) != 0:              # capacity overflow: grow and redo this request, in order
+            torch.cuda.synchronize(self.device)
+            self.engine._reserve(int(int(self.h_status[k][0]) * 1.25) + 1024)
+            t = self.submit(*req)
+            return self.wait(t)
+        return req[-1]
+
+    def project(self, *request):
+        return self.wait(self.submit(*request))
+
+    def drain(self):
+        for t in sorted(self._pending):
+            self.wait(t)

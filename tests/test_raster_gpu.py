@@ -129,3 +129,37 @@ def test_async_capacity_overflow_is_reported_and_recovered():
     assert ve.check() is False
     assert ve.fit(*vargs) == vref["R"]
     assert np.abs(ve.out.cpu().numpy().astype(np.float64) - vref["vol"]).max() <= 1e-5 * np.abs(vref["vol"]).max() + 1e-7
+
+
+def test_host_projector_pipeline_matches_direct_forward():
+    """HostProjector (pinned host in / out, three-stream pipeline, deferred capacity check) returns exactly what a
+    plain forward returns, for interleaved views, and recovers from a capacity overflow."""
+    import torch
+    from r2_gaussian_b200 import scene
+    from r2_gaussian_b200.engine import HostProjector, RasterEngine
+    cloud, _ = util.case("cone_trained_mid")
+    scanner = scene.cone_beam_scanner(128)
+    views = scene.make_views(scanner, 6)
+    P, W, H = cloud.P, 128, 128
+    dev = torch.device("cuda")
+    pin = lambda a: torch.tensor(a).pin_memory()
+    hm, hd, hs, hr = pin(cloud.means), pin(cloud.density), pin(cloud.scales), pin(cloud.rotations)
+    hv = [(pin(v.viewmatrix), pin(v.projmatrix), pin(v.campos), v) for v in views]
+    eng = RasterEngine(P, W, H, dev)
+    dm, dd, ds, dr = (t.to(dev) for t in (hm, hd, hs, hr))
+    want = []
+    for a, b, c, v in hv:
+        eng.fit(dm, dd, ds, dr, a.to(dev), b.to(dev), c.to(dev), v.tanfovx, v.tanfovy, v.mode)
+        want.append(eng.out.clone().cpu())
+    hp = HostProjector(P, W, H, dev, depth=3, capacity=64)     # far too small: the first requests overflow
+    outs = [torch.empty((1, H, W)).pin_memory() for _ in range(12)]
+    tickets = []
+    for i in range(12):
+        a, b, c, v = hv[i % 6]
+        tickets.append(hp.submit(hm, hd, hs, hr, a, b, c, v.tanfovx, v.tanfovy, v.mode, outs[i]))
+    hp.drain()
+    for i in range(12):
+        assert torch.equal(outs[i], want[i % 6]), i
+    a, b, c, v = hv[3]
+    got = hp.project(hm, hd, hs, hr, a, b, c, v.tanfovx, v.tanfovy, v.mode, outs[0])
+    assert torch.equal(got, want[3])
