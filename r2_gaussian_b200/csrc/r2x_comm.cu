@@ -54,14 +54,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerPack pk, int wo
         }
     }
     __syncthreads();
-    // 3. ordered sum
+    // 3. ordered sum.  All peer loads of an element are issued before the first add (the adds wait on the loads'
+    //    scoreboards in program order: interleaving load/add would serialise the NVLink round trips).
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 acc = ld_volatile_f4(reinterpret_cast<const float4*>(pk.buf[0]) + i);
-        for (int p = 1; p < world; ++p) {
-            const float4 v = ld_volatile_f4(reinterpret_cast<const float4*>(pk.buf[p]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+        float4 v[R2X_MAX_PEERS];
+#pragma unroll
+        for (int p = 0; p < R2X_MAX_PEERS; ++p)
+            if (p < world) v[p] = ld_volatile_f4(reinterpret_cast<const float4*>(pk.buf[p]) + i);
+        float4 acc = v[0];
+#pragma unroll
+        for (int p = 1; p < R2X_MAX_PEERS; ++p)
+            if (p < world) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
         reinterpret_cast<float4*>(out)[i] = acc;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
