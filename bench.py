@@ -319,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_render * 1e3, "peak_source": peak_src,
                 "pair_evals_per_launch": pairs, "pair_evals_per_s": pairs / t_render,
-                "note": "kernel is FP32-issue/MUFU-bound (about 8.5 issue slots incl. 1 MUFU.EX2 per pixel-Gaussian "
+                "note": "kernel is MUFU/FP32-issue-bound (8 issue slots incl. 1 MUFU.EX2 per pixel-Gaussian "
                         "pair), not HBM-bound; see DESIGN.md section 5"}
 
     result = {
