@@ -10,18 +10,23 @@ ours arm
   value     projections/s with every input resident in HBM: K steps through the asynchronous C ABI
             (r2x_raster_forward_async, no host synchronisation), each step bracketed by its own pair of CUDA
             events with L2 flushed (256 MiB memset) between steps; value = K / sum(step durations); for N > 1
-            the Gaussians are sharded across ranks and each step includes the NCCL all-reduce of the detector
-            image; the per-rank sums are max-reduced over ranks.
-  e2e       the same metric through the public plugin call a user makes (GaussianRasterizer, the reference's
-            Python surface): every step copies the Gaussian parameters + view matrices host->device from
-            pinned memory and reads the image back device->host; wall clock around the K steps.
+            the Gaussians are sharded across ranks and each step includes the exchange of the detector image
+            (--reduce p2p: one kernel over NVLink peer memory, r2x_peer_allreduce_sum; --reduce nccl:
+            dist.all_reduce); the per-rank sums are max-reduced over ranks.
+  e2e       the same metric with HOST buffers through the public API (engine.HostProjector.project): every step
+            copies the Gaussian parameters + view matrices host->device from pinned memory, runs the 4 kernels
+            and reads the image back device->host, one request at a time; wall clock around the K steps.
+            pipelined_value = the same requests through HostProjector.submit()/wait() (copies of neighbouring
+            requests overlap the kernels); autograd_module_value = through GaussianRasterizer, the reference's
+            Python surface (used for N > 1, where the per-rank images are summed on the device first).
   roofline  the dominant kernel (raster_render_kernel) re-run alone on the forward's state
             (r2x_raster_render_only), CUDA events, L2 flushed; achieved = (32 R + 4 N) bytes / duration
             against the measured HBM copy peak (MEASURED_PEAKS.json).  The kernel is FP32/MUFU-bound, not
             HBM-bound, so the fraction is small by construction; the FP32-issue fraction is
             reported beside it.
   cpu_baseline  the CPU oracle port (oracle/r2_oracle.c, OpenMP) on the host cores, 2 projections of the
-            same scene.
+            same scene; cpu_baseline_torch = the pure-PyTorch CPU additive projector of SURVEY 8(d)
+            (oracle/torch_projector.py), 3 projections.
 
 reference arm (--impl reference)
   The reference has no CPU implementation of this path: its "own implementation" IS a CUDA rasterizer.  The
@@ -192,6 +197,26 @@ def cpu_baseline(cloud, views, n_proj=2):
     return {"value": n_proj / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
             "sample": f"{n_proj} full projections of the same scene ({cloud.P} Gaussians, "
                       f"{views[0].image_width}x{views[0].image_height}), oracle/r2_oracle.c with OpenMP"}
+
+
+def cpu_baseline_torch(cloud, views, n_proj=3):
+    """SURVEY 8(d)'s CPU baseline: the pure-PyTorch additive projector (oracle/torch_projector.py) on all host cores."""
+    import torch
+
+    from oracle import torch_projector as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    v = views[0]
+    tp.project(cloud.means, cloud.density, cloud.scales, cloud.rotations, v.viewmatrix, v.projmatrix, v.image_width,
+               v.image_height, v.tanfovx, v.tanfovy, v.mode)            # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for i in range(n_proj):
+        v = views[(i + 1) % len(views)]
+        tp.project(cloud.means, cloud.density, cloud.scales, cloud.rotations, v.viewmatrix, v.projmatrix,
+                   v.image_width, v.image_height, v.tanfovx, v.tanfovy, v.mode)
+    dt = time.perf_counter() - t0
+    return {"value": n_proj / dt, "unit": UNIT, "cores": cores, "kind": "pure-PyTorch CPU additive projector",
+            "sample": f"{n_proj} full projections of the same scene after one warm-up projection"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -412,6 +437,7 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cloud, views, 2)
+        result["cpu_baseline_torch"] = cpu_baseline_torch(cloud, views, 3)
     return result
 
 

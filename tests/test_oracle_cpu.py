@@ -178,3 +178,15 @@ def test_knn_oracle_vs_kdtree():
         assert np.allclose(got, ref, rtol=2e-6, atol=1e-12)
     two = orc.knn3_mean_dist2(np.zeros((2, 3), np.float32))
     assert np.all(two > 1e37)          # fewer than 3 neighbours: FLT_MAX placeholders, as upstream
+
+
+@pytest.mark.parametrize("name", ["cone_trained_mid", "parallel_trained_small", "cone_trained_ragged"])
+def test_torch_cpu_projector_matches_oracle(name):
+    """The pure-PyTorch CPU projector (bench.py's cpu_baseline_torch) against the C oracle."""
+    from oracle import torch_projector as tp
+    cloud, view = util.case(name)
+    ref = np.asarray(util.oracle_raster_forward(cloud, view)["image"])
+    got = tp.project(cloud.means, cloud.density, cloud.scales, cloud.rotations, view.viewmatrix, view.projmatrix,
+                     view.image_width, view.image_height, view.tanfovx, view.tanfovy, view.mode).numpy()
+    assert got.shape == (1, view.image_height, view.image_width)
+    assert np.abs(got - ref.reshape(got.shape)).max() <= 1e-4 * np.abs(ref).max()
