@@ -1,0 +1,245 @@
+"""Training / evaluation driver with the flow and defaults of the reference's `train.py:36-240` and
+`arguments/__init__.py:21-71`, built from this repository's pieces: `dataset.Scene`, `GaussianModel`,
+`render()` / `query()`, the fused loss kernels and `FusedAdam`.
+
+    python -m r2_gaussian_b200.trainer -s <scene dir or NAF pickle> -m <output dir> [--iterations N] [...]
+
+Same order of random draws as the reference (camera: `random.randint` on a stack refilled when empty,
+`train.py:103-106`; TV crop centre: CPU `torch.rand(3)`, `train.py:130-132`), same densification schedule and
+thresholds (expressed relative to the volume size), same checkpoint tuple and `point_cloud.pickle` export.  Not
+carried over: TensorBoard / matplotlib logging (absent from this image).  GPU only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import time
+from dataclasses import asdict, dataclass
+
+import numpy as np
+import torch
+
+from . import losses
+from .dataset import Scene
+from .gaussian_model import GaussianModel
+from .metrics import metric_proj, metric_vol
+from .render_query import query, render
+
+
+@dataclass
+class ModelParams:
+    source_path: str = ""
+    model_path: str = ""
+    data_device: str = "cuda"
+    ply_path: str = ""           # initial cloud (.npy [N,4]); default: <source>/init_<name>.npy
+    scale_min: float = 0.0005    # fraction of the volume size
+    scale_max: float = 0.5
+    eval: bool = True
+
+
+@dataclass
+class PipelineParams:
+    compute_cov3D_python: bool = False
+    debug: bool = False
+
+
+@dataclass
+class OptimizationParams:
+    iterations: int = 30_000
+    position_lr_init: float = 0.0002
+    position_lr_final: float = 0.00002
+    position_lr_max_steps: int = 30_000
+    density_lr_init: float = 0.01
+    density_lr_final: float = 0.001
+    density_lr_max_steps: int = 30_000
+    scaling_lr_init: float = 0.005
+    scaling_lr_final: float = 0.0005
+    scaling_lr_max_steps: int = 30_000
+    rotation_lr_init: float = 0.001
+    rotation_lr_final: float = 0.0001
+    rotation_lr_max_steps: int = 30_000
+    lambda_dssim: float = 0.25
+    lambda_tv: float = 0.05
+    tv_vol_size: int = 32
+    density_min_threshold: float = 0.00001
+    densification_interval: int = 100
+    densify_from_iter: int = 500
+    densify_until_iter: int = 15000
+    densify_grad_threshold: float = 5.0e-5
+    densify_scale_threshold: float | None = 0.1     # fraction of the volume size
+    max_screen_size: float | None = None
+    max_scale: float | None = None                  # fraction of the volume size
+    max_num_gaussians: int | None = 500_000
+
+
+def default_init_path(source_path: str) -> str:
+    """`<scene>/init_<scene>.npy` for directories, `<dir>/init_<stem>.npy` for NAF pickles (`initialize.py:29-41`)."""
+    if os.path.exists(os.path.join(source_path, "meta_data.json")):
+        return os.path.join(source_path, "init_" + os.path.basename(source_path.rstrip("/")) + ".npy")
+    if source_path.split(".")[-1] in ("pickle", "pkl"):
+        return os.path.join(os.path.dirname(source_path), "init_" + os.path.basename(source_path).split(".")[0] + ".npy")
+    raise ValueError("Could not recognize scene type!")
+
+
+def derived_settings(scanner_cfg: dict, model: ModelParams, opt: OptimizationParams) -> dict:
+    """Volume-relative thresholds in world units (`train.py:50-62`, `:87-90`)."""
+    to_world = max(scanner_cfg["sVoxel"])
+    scale_bound = None
+    if model.scale_min > 0 and model.scale_max > 0:
+        scale_bound = np.array([model.scale_min, model.scale_max]) * to_world
+    n = int(opt.tv_vol_size)
+    return {"volume_to_world": to_world,
+            "max_scale": opt.max_scale * to_world if opt.max_scale else None,
+            "densify_scale_threshold": opt.densify_scale_threshold * to_world if opt.densify_scale_threshold else None,
+            "scale_bound": scale_bound,
+            "tv_vol_nVoxel": [n, n, n],
+            "tv_vol_sVoxel": [float(d) * n for d in scanner_cfg["dVoxel"]]}
+
+
+@torch.no_grad()
+def evaluate(scene: Scene, gaussians: GaussianModel, pipe, with_ssim: bool = True) -> dict:
+    """3-D PSNR / SSIM of the queried volume and 2-D PSNR / SSIM of the rendered train and test views, with the
+    reference's metric definitions (`train.py:262-330`, `utils/image_utils.py:90-183`)."""
+    cfg = scene.scanner_cfg
+    vol = query(gaussians, cfg["offOrigin"], cfg["nVoxel"], cfg["sVoxel"], pipe)["vol"]
+    out = {"psnr_3d": metric_vol(scene.vol_gt, vol, "psnr")[0]}
+    if with_ssim:
+        out["ssim_3d"] = metric_vol(scene.vol_gt, vol, "ssim")[0]
+    for name, cams in (("train", scene.getTrainCameras()), ("test", scene.getTestCameras())):
+        if not cams:
+            continue
+        imgs = torch.concat([render(c, gaussians, pipe)["render"] for c in cams], 0).permute(1, 2, 0)
+        gts = torch.concat([c.original_image.to(imgs.device) for c in cams], 0).permute(1, 2, 0)
+        out[f"psnr_2d_{name}"] = metric_proj(gts, imgs, "psnr")[0]
+        if with_ssim:
+            out[f"ssim_2d_{name}"] = metric_proj(gts, imgs, "ssim")[0]
+    return out
+
+
+def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, testing_iterations=(),
+             saving_iterations=(), checkpoint_iterations=(), checkpoint: str | None = None, init_points=None,
+             log=print) -> dict:
+    first_iter = 0
+    scene = Scene(model.source_path, model.model_path, eval=model.eval, shuffle=False, device="cuda",
+                  data_device=model.data_device)
+    cfg = scene.scanner_cfg
+    bbox_cpu = scene.bbox.float()
+    bbox = bbox_cpu.cuda()
+    ds = derived_settings(cfg, model, opt)
+    queryfunc = lambda g: query(g, cfg["offOrigin"], cfg["nVoxel"], cfg["sVoxel"], pipe)
+
+    gaussians = GaussianModel(ds["scale_bound"])
+    if init_points is None:
+        path = model.ply_path or default_init_path(model.source_path)
+        assert os.path.exists(path), f"Cannot find {path} for initialization."
+        init_points = np.load(path)
+    gaussians.create_from_pcd(init_points[:, :3], init_points[:, 3:4], 1.0)
+    scene.gaussians = gaussians
+    gaussians.training_setup(opt)
+    if checkpoint is not None:
+        model_state, first_iter = torch.load(checkpoint, weights_only=False)
+        gaussians.restore(model_state, opt)
+        log(f"Load checkpoint {os.path.basename(checkpoint)}.")
+
+    use_tv = opt.lambda_tv > 0
+    tv_n = ds["tv_vol_nVoxel"]
+    tv_s = torch.tensor(ds["tv_vol_sVoxel"])
+    ckpt_dir = os.path.join(scene.model_path, "ckpt")
+    if scene.model_path:
+        os.makedirs(ckpt_dir, exist_ok=True)
+    history = {"eval": {}, "loss": []}
+    stack = None
+    torch.cuda.synchronize()
+    t_start = time.perf_counter()
+    for iteration in range(first_iter + 1, opt.iterations + 1):
+        gaussians.update_learning_rate(iteration)
+        if not stack:
+            stack = scene.getTrainCameras().copy()
+        cam = stack.pop(random.randint(0, len(stack) - 1))
+
+        pkg = render(cam, gaussians, pipe)
+        gt = cam.original_image.cuda()
+        loss = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)
+        total = loss["total"]
+        if use_tv:
+            centre = (bbox_cpu[0] + tv_s / 2) + (bbox_cpu[1] - tv_s - bbox_cpu[0]) * torch.rand(3)
+            vol = query(gaussians, centre, tv_n, tv_s, pipe)["vol"]
+            total = total + opt.lambda_tv * losses.tv_3d_loss(vol, reduction="mean")
+        total.backward()
+
+        with torch.no_grad():
+            gaussians.update_max_radii(pkg["radii"], pkg["visibility_filter"])
+            gaussians.add_densification_stats(pkg["viewspace_points"], pkg["visibility_filter"])
+            if iteration < opt.densify_until_iter and iteration > opt.densify_from_iter \
+                    and iteration % opt.densification_interval == 0:
+                gaussians.densify_and_prune(opt.densify_grad_threshold, opt.density_min_threshold, opt.max_screen_size,
+                                            ds["max_scale"], opt.max_num_gaussians, ds["densify_scale_threshold"], bbox)
+            if gaussians.get_density.shape[0] == 0:
+                raise ValueError("No Gaussian left. Change adaptive control hyperparameters!")
+            if iteration < opt.iterations:
+                gaussians.optimizer.step()
+                gaussians.optimizer.zero_grad(set_to_none=True)
+            if scene.model_path and (iteration in saving_iterations or iteration == opt.iterations):
+                log(f"[ITER {iteration}] Saving Gaussians")
+                scene.save(iteration, queryfunc)
+            if scene.model_path and iteration in checkpoint_iterations:
+                log(f"[ITER {iteration}] Saving Checkpoint")
+                torch.save((gaussians.capture(), iteration), os.path.join(ckpt_dir, f"chkpnt{iteration}.pth"))
+            if iteration % 100 == 0:
+                history["loss"].append((iteration, float(total)))
+            if iteration in testing_iterations:
+                history["eval"][iteration] = evaluate(scene, gaussians, pipe)
+                log(f"[ITER {iteration}] {history['eval'][iteration]}  points {gaussians.get_xyz.shape[0]}")
+    torch.cuda.synchronize()
+    history["seconds"] = time.perf_counter() - t_start
+    history["iterations"] = opt.iterations - first_iter
+    history["gaussians"] = int(gaussians.get_xyz.shape[0])
+    history["scene"], history["model"] = scene, gaussians
+    return history
+
+
+def _add_dataclass_args(parser, cls, skip=()):
+    for name, f in cls.__dataclass_fields__.items():
+        if name in skip:
+            continue
+        default = f.default
+        if isinstance(default, bool):
+            parser.add_argument("--" + name, default=default, action="store_true")
+        else:
+            typ = float if (default is None or isinstance(default, float)) else type(default)
+            parser.add_argument("--" + name, default=default, type=typ)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Train R2-Gaussian on one scene (B200-native pipeline)")
+    ap.add_argument("-s", "--source_path", required=True)
+    ap.add_argument("-m", "--model_path", default="")
+    _add_dataclass_args(ap, ModelParams, skip=("source_path", "model_path"))
+    _add_dataclass_args(ap, PipelineParams)
+    _add_dataclass_args(ap, OptimizationParams)
+    ap.add_argument("--test_iterations", nargs="+", type=int, default=[5000, 10000, 20000, 30000])
+    ap.add_argument("--save_iterations", nargs="+", type=int, default=[])
+    ap.add_argument("--checkpoint_iterations", nargs="+", type=int, default=[])
+    ap.add_argument("--start_checkpoint", type=str, default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args(argv)
+    pick = lambda cls: cls(**{k: getattr(a, k) for k in cls.__dataclass_fields__})
+    model, pipe, opt = pick(ModelParams), pick(PipelineParams), pick(OptimizationParams)
+    model.source_path = os.path.abspath(model.source_path)
+    if not model.model_path:
+        model.model_path = os.path.join("./output", os.path.basename(model.source_path.rstrip("/")))
+    os.makedirs(model.model_path, exist_ok=True)
+    with open(os.path.join(model.model_path, "cfg_args.json"), "w") as f:
+        json.dump({"model": asdict(model), "pipe": asdict(pipe), "opt": asdict(opt)}, f, indent=1)
+    random.seed(a.seed), np.random.seed(a.seed), torch.manual_seed(a.seed)     # safe_state (`general_utils.py:61-63`)
+    hist = training(model, opt, pipe, set(a.test_iterations) | {opt.iterations}, set(a.save_iterations),
+                    set(a.checkpoint_iterations), a.start_checkpoint)
+    final = hist["eval"].get(opt.iterations, {})
+    print(json.dumps({"seconds": hist["seconds"], "ms_per_iteration": hist["seconds"] / max(hist["iterations"], 1) * 1e3,
+                      "gaussians": hist["gaussians"], **final}))
+
+
+if __name__ == "__main__":
+    main()
