@@ -270,7 +270,16 @@ def run_ours(args, rank, world, local_rank):
     reducer = None
     if world > 1 and args.reduce == "p2p":
         from r2_gaussian_b200.peer import PeerReducer
-        reducer = PeerReducer(W * H, dev)
+        try:
+            reducer = PeerReducer(W * H, dev)
+            ok = 1
+        except Exception as e:  # e.g. no peer access between these GPUs: agree on NCCL, loudly
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using NCCL", file=sys.stderr, flush=True)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            reducer, args.reduce = None, "nccl"
     final = torch.empty((1, H, W), dtype=torch.float32, device=dev)
 
     def step(i):
