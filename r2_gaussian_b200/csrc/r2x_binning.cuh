@@ -25,7 +25,7 @@ struct BinningView {
     uint32_t* vals[2];     // original instance index, ping-pong
     uint32_t* inst_g;      // [R] Gaussian id of instance i (emission order)
     uint32_t* point_list;  // [R] Gaussian id at sorted position s
-    uint32_t* inst_pos;    // [R] emission-order index i of the instance at sorted position s
+    uint32_t* inst_pos;    // [R] emission-order slot of the instance at tile-major position s (backward moments)
     uint32_t* hist;        // [256 * SORT_MAX_BLOCKS] digit-major per-block histograms
     uint2* extra_item;     // TilePlan::extra_item
     float* partial;        // TilePlan::partial

@@ -5,12 +5,14 @@
 //
 // Same machinery as r2x_raster.cu with 8x8x8 tiles:
 //   voxel_preprocess_kernel  per Gaussian, TMA-staged parameters, bit-exact radii / cube / tiles_touched.
-//   voxel_render_kernel      one CTA per tile, 256 threads = 4 list slices x 64 (x,y) columns; each thread
+//   voxel_render_kernel      persistent CTAs pull (tile, chunk of <= 256 instances) work items from the atomic
+//                            queue of the work plan; 256 threads = 4 list slices x 64 (x,y) columns; each thread
 //                            owns the 8 voxels of a z column (contiguous in memory): the x/y part of the
-//                            quadratic form is computed once per Gaussian and column.
+//                            quadratic form is computed once per Gaussian and column, the z part runs by
+//                            forward differences (exact Horner path for flagged Gaussians).
 //   voxel_render_bwd_kernel  one thread per (tile, Gaussian) instance, loops over the 512 voxels and keeps
-//                            the ten weighted moments in registers; no atomics.
-//   voxel_gauss_bwd_kernel   per Gaussian: fixed-order sum of instance moments + chain rule.
+//                            the ten weighted moments in registers; no atomics; emission-order slots.
+//   voxel_gauss_bwd_kernel   per Gaussian: fixed-order sum of its (contiguous) instance moments + chain rule.
 #include "r2x_voxel.cuh"
 
 namespace r2x {
