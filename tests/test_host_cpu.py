@@ -113,3 +113,37 @@ def test_render_query_surface_with_stub_model():
     cam.mode = 2
     with pytest.raises(ValueError):
         render(cam, pc, pipe)
+
+
+def test_gaussian_utils_match_their_definitions():
+    """Helpers behind GaussianModel (r2_gaussian/utils/gaussian_utils.py:5-90): pure torch, checked on the CPU."""
+    import math
+
+    from r2_gaussian_b200 import gaussian_utils as gu
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(64, 4, generator=g)
+    R = gu.build_rotation(q)
+    eye = torch.eye(3).expand(64, 3, 3)
+    assert torch.allclose(R @ R.transpose(1, 2), eye, atol=1e-5) and torch.allclose(torch.linalg.det(R), torch.ones(64), atol=1e-5)
+    assert torch.allclose(gu.build_rotation(3.0 * q), R, atol=1e-6)              # normalises its input
+    ident = gu.build_rotation(torch.tensor([[1.0, 0, 0, 0]]))
+    assert torch.equal(ident[0], torch.eye(3))
+    # 90 degrees about z: x -> y
+    rz = gu.build_rotation(torch.tensor([[math.cos(math.pi / 4), 0, 0, math.sin(math.pi / 4)]]))
+    assert torch.allclose(rz[0] @ torch.tensor([1.0, 0, 0]), torch.tensor([0.0, 1.0, 0]), atol=1e-6)
+    s = torch.rand(64, 3, generator=g) + 0.1
+    L = gu.build_scaling_rotation(s, q)
+    assert torch.allclose(L, R @ torch.diag_embed(s), atol=1e-6)
+    cov = L @ L.transpose(1, 2)
+    six = gu.strip_symmetric(cov)
+    assert torch.equal(six[:, 0], cov[:, 0, 0]) and torch.equal(six[:, 4], cov[:, 1, 2]) and six.shape == (64, 6)
+    x = torch.rand(100, generator=g) * 3 + 1e-3
+    assert torch.allclose(torch.nn.functional.softplus(gu.inverse_softplus(x)), x, rtol=1e-5, atol=1e-6)
+    p = torch.rand(100, generator=g) * 0.98 + 0.01
+    assert torch.allclose(torch.sigmoid(gu.inverse_sigmoid(p)), p, atol=1e-6)
+    f = gu.get_expon_lr_func(2e-4, 2e-6, max_steps=1000)
+    assert abs(f(0) - 2e-4) < 1e-18 and abs(f(1000) - 2e-6) < 1e-18 and abs(f(5000) - 2e-6) < 1e-18
+    assert abs(f(500) - math.sqrt(2e-4 * 2e-6)) < 1e-15 and f(-1) == 0.0
+    assert gu.get_expon_lr_func(0.0, 0.0)(10) == 0.0
+    d = gu.get_expon_lr_func(1e-2, 1e-2, lr_delay_steps=100, lr_delay_mult=0.1, max_steps=1000)
+    assert abs(d(0) - 1e-3) < 1e-12 and abs(d(100) - 1e-2) < 1e-12 and d(50) < 1e-2
