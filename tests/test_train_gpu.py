@@ -368,3 +368,34 @@ def test_densification_stats_without_mask_indexing():
     ref = before.clone()
     ref[vis] = torch.max(ref[vis], radii[vis].float())
     assert torch.equal(gm.max_radii2D, ref)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fused_losses_against_reference_golden_vectors(tag):
+    """The fused L1 + D-SSIM kernel and the TV kernel against outputs of the reference's own loss_utils.py
+    (float64 evaluation; tests/golden/make_golden_host.py)."""
+    import os
+    from r2_gaussian_b200 import losses
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_golden.npz"))
+    img = torch.from_numpy(G[f"loss_{tag}_img"]).cuda().requires_grad_(True)
+    gt = torch.from_numpy(G[f"loss_{tag}_gt"]).cuda()
+    l1_64, ssim_64, total_64 = G[f"loss_{tag}_f64"]
+    ssim_32 = G[f"loss_{tag}_f32"][1]
+    out = losses.image_loss(img, gt, lambda_dssim=0.25)
+    out["total"].backward()
+    bar = max(5e-6, 3.0 * abs(ssim_32 - ssim_64))               # the reference's own float32 error sets the scale
+    assert abs(out["render"].item() - l1_64) <= 1e-6
+    assert abs((1.0 - out["dssim"].item()) - ssim_64) <= bar
+    assert abs(out["total"].item() - total_64) <= 2e-6 + 0.25 * bar
+    g64, g32 = G[f"loss_{tag}_grad_f64"], G[f"loss_{tag}_grad_f32"]
+    gbar = max(2e-4 * np.abs(g64).max(), 3.0 * np.abs(g32 - g64).max())
+    assert np.abs(img.grad.cpu().numpy() - g64).max() <= gbar
+    if tag in ("a", "b"):
+        for red in ("sum", "mean"):
+            v = torch.from_numpy(G[f"tv_{tag}_vol"]).cuda().requires_grad_(True)
+            t = losses.tv_3d_loss(v, reduction=red)
+            t.backward()
+            want = float(G[f"tv_{tag}_{red}"][0])
+            assert abs(t.item() - want) <= 2e-6 * max(1.0, abs(want))
+            gw = G[f"tv_{tag}_{red}_grad"]
+            assert np.abs(v.grad.cpu().numpy() - gw).max() <= 1e-6 * max(1.0, np.abs(gw).max())
