@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: scene geometry, the Python surface (names / fields / argument
 validation identical to the reference's), sharding arithmetic, and the no-fallback rule."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -147,3 +148,22 @@ def test_gaussian_utils_match_their_definitions():
     assert gu.get_expon_lr_func(0.0, 0.0)(10) == 0.0
     d = gu.get_expon_lr_func(1e-2, 1e-2, lr_delay_steps=100, lr_delay_mult=0.1, max_steps=1000)
     assert abs(d(0) - 1e-3) < 1e-12 and abs(d(100) - 1e-2) < 1e-12 and d(50) < 1e-2
+
+
+def test_bench_reference_arm_json_contract_on_cpu():
+    """`bench.py --impl reference` without a GPU falls back to the CPU oracle and still prints the contract's line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--gaussians", "3000", "--detector", "64", "--views", "2"], capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "projections_per_sec" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
