@@ -145,3 +145,33 @@ def test_trainer_settings_and_cli_defaults(tmp_path):
     assert trainer.default_init_path("/data/foot_50.pickle") == "/data/init_foot_50.npy"
     with pytest.raises(ValueError):
         trainer.default_init_path("/data/unknown.bin")
+
+
+def test_initialize_pcd_cli_random_mode(tmp_path):
+    """BASELINE configs[0]: `initialize_pcd --recon_method random --n_points 1000` on a 64^3 synthetic phantom,
+    CPU only."""
+    from r2_gaussian_b200 import initialize_pcd
+    rng = np.random.default_rng(3)
+    sc = _scanner(det=16, vox=64)
+    vol = np.zeros((64, 64, 64), np.float32)
+    vol[16:48, 20:44, 24:40] = 0.6
+    frames = [(a, rng.random((16, 16)).astype(np.float32)) for a in np.linspace(0, 2 * math.pi, 5)[:-1]]
+    case = tmp_path / "phantom"
+    dataset.write_blender(str(case), sc, frames, [], vol)
+    out = initialize_pcd.main(["--data", str(case), "--recon_method", "random", "--n_points", "1000"])
+    assert out == str(case / "init_phantom.npy")
+    pts = np.load(out)
+    np.random.seed(0)
+    want_xyz = 2.0 * (np.random.rand(1000, 3) - 0.5)            # offOrigin 0, scaled sVoxel 2 (initialize_pcd.py:50-58)
+    want_rho = np.random.rand(1000)
+    assert pts.shape == (1000, 4) and np.allclose(pts[:, :3], want_xyz) and np.allclose(pts[:, 3], want_rho)
+    with pytest.raises(SystemExit):
+        initialize_pcd.main(["--data", str(case), "--recon_method", "random", "--n_points", "10"])   # file exists
+    np.save(tmp_path / "recon.npy", vol)
+    out2 = initialize_pcd.main(["--data", str(case), "--recon_method", "volume", "--recon", str(tmp_path / "recon.npy"),
+                                "--n_points", "500", "--output", str(tmp_path / "init2.npy")])
+    p2 = np.load(out2)
+    assert p2.shape == (500, 4) and np.allclose(p2[:, 3], 0.6 * 0.15)
+    assert p2[:, 0].min() >= 16 / 32 - 1 - 1e-9 and p2[:, 0].max() <= 47 / 32 - 1 + 1e-9
+    with pytest.raises(SystemExit):
+        initialize_pcd.main(["--data", str(case), "--recon_method", "fdk", "--output", str(tmp_path / "x.npy")])
