@@ -355,6 +355,14 @@ def run_ours(args, rank, world, local_rank):
                 "pair_evals_per_launch": pairs, "pair_evals_per_s": pairs / t_render,
                 "note": "kernel is MUFU/FP32-issue-bound (8 issue slots incl. 1 MUFU.EX2 per pixel-Gaussian "
                         "pair), not HBM-bound; see DESIGN.md section 5"}
+    try:   # the bound that does apply: one MUFU.EX2 per pair; 15.85 ex2/clk/SM measured (scripts/micro/mufu_rate.cu)
+        props = torch.cuda.get_device_properties(dev)
+        mhz = float(sampler.summary().get("sm_mhz") or 0.0) or 1965.0
+        ex2_peak = 15.85 * props.multi_processor_count * mhz * 1e6
+        roofline["mufu"] = {"achieved": pairs / t_render, "peak": ex2_peak, "unit": "ex2/s", "frac": pairs / t_render / ex2_peak,
+                            "peak_source": f"15.85 ex2/clk/SM (measured) x {props.multi_processor_count} SMs x {mhz:.0f} MHz"}
+    except Exception as e:   # informational only
+        roofline["mufu"] = {"error": str(e)}
 
     result = {
         "metric": METRIC, "value": args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
