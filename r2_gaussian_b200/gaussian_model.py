@@ -98,12 +98,16 @@ class GaussianModel:
         self.setup_functions()
 
     # ------------------------------------------------------------------ initialisation
-    def create_from_pcd(self, xyz, density, spatial_lr_scale: float):
+    def create_from_pcd(self, xyz, density, spatial_lr_scale: float, dist2=None):
+        """`dist2` (optional, not in the reference): precomputed mean squared 3-NN distances for these points --
+        a Gaussian-sharded run computes them on the FULL cloud before splitting it, so that the initial scales do
+        not depend on the number of ranks."""
         self.spatial_lr_scale = spatial_lr_scale
         points = torch.as_tensor(np.asarray(xyz)).float().cuda()
         print("Initialize gaussians from {} estimated points".format(points.shape[0]))
         raw_density = self.density_inverse_activation(torch.as_tensor(np.asarray(density))).float().cuda()
-        dist = torch.sqrt(torch.clamp_min(distCUDA2(points), 0.001 ** 2))
+        nn2 = distCUDA2(points) if dist2 is None else torch.as_tensor(np.asarray(dist2)).float().cuda().reshape(-1)
+        dist = torch.sqrt(torch.clamp_min(nn2, 0.001 ** 2))
         if self.scale_bound is not None:
             dist = torch.clamp(dist, self.scale_bound[0] + EPS, self.scale_bound[1] - EPS)   # keep the inverse finite
         raw_scale = self.scaling_inverse_activation(dist)[..., None].repeat(1, 3)

@@ -107,3 +107,36 @@ def sharded_query(query_fn: Callable[..., dict], *args, group=None, **kw) -> dic
     out = dict(query_fn(*args, **kw))
     out["vol"] = all_reduce_sum(out["vol"], group)
     return out
+
+
+# ---- Gaussian-sharded training: host-side helpers -----------------------------------------------------------
+def shard_init_points(points, dist2, rank: int, world: int):
+    """Rank r's contiguous slice of an initial cloud [N,4] (x,y,z,density) and of the mean squared 3-NN distances
+    computed on the FULL cloud (so the initial scales are independent of the number of ranks)."""
+    lo, hi = shard_bounds(len(points), rank, world)
+    return points[lo:hi], (None if dist2 is None else dist2[lo:hi])
+
+
+def merge_point_clouds(parts: list) -> dict:
+    """Concatenate per-rank `save_ply` dictionaries (xyz / density / scale / rotation / scale_bound) in rank order
+    into the single point cloud the reference's `test.py` expects."""
+    import numpy as np
+    if not parts:
+        raise ValueError("merge_point_clouds: nothing to merge")
+    out = {k: np.concatenate([np.asarray(p[k]) for p in parts], axis=0) for k in ("xyz", "density", "scale", "rotation")}
+    out["scale_bound"] = parts[0]["scale_bound"]
+    return out
+
+
+def gather_point_cloud(gaussians, group=None):
+    """All ranks call; rank 0 receives the merged dictionary (others None).  Uses object collectives: meant for the
+    infrequent save / export steps, not for the training loop."""
+    part = {"xyz": gaussians._xyz.detach().cpu().numpy(), "density": gaussians._density.detach().cpu().numpy(),
+            "scale": gaussians._scaling.detach().cpu().numpy(), "rotation": gaussians._rotation.detach().cpu().numpy(),
+            "scale_bound": gaussians.scale_bound}
+    rank, world = world_info()
+    if world == 1:
+        return part
+    parts = [None] * world
+    dist.all_gather_object(parts, part, group=group)
+    return merge_point_clouds(parts) if rank == 0 else None

@@ -8,6 +8,11 @@ Same order of random draws as the reference (camera: `random.randint` on a stack
 `train.py:103-106`; TV crop centre: CPU `torch.rand(3)`, `train.py:130-132`), same densification schedule and
 thresholds (expressed relative to the volume size), same checkpoint tuple and `point_cloud.pickle` export.  Not
 carried over: TensorBoard / matplotlib logging (absent from this image).  GPU only.
+
+Under `torchrun --nproc-per-node N` the same command trains Gaussian-sharded: every rank owns an index slice of the
+cloud with its own Adam state and densification (budget `max_num_gaussians / N`), `render()` / `query()` sum the
+partial images / volumes over the ranks (NCCL, or the peer-memory kernel with `--peer_exchange`), the host RNG
+streams stay in lock-step (same seed, same draws), rank 0 writes one merged `point_cloud.pickle`.
 """
 from __future__ import annotations
 
@@ -26,6 +31,7 @@ from .dataset import Scene
 from .gaussian_model import GaussianModel
 from .metrics import metric_proj, metric_vol
 from .render_query import query, render
+from .sharded import gather_point_cloud, shard_init_points, world_info
 
 
 @dataclass
@@ -135,7 +141,18 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
         path = model.ply_path or default_init_path(model.source_path)
         assert os.path.exists(path), f"Cannot find {path} for initialization."
         init_points = np.load(path)
-    gaussians.create_from_pcd(init_points[:, :3], init_points[:, 3:4], 1.0)
+    rank, world = world_info()
+    dist2 = None
+    if world > 1:
+        # Gaussian-sharded run (one process per GPU, torchrun): every rank owns an index slice of the cloud, its
+        # Adam state and its densification; render() / query() sum the partial images / volumes over the ranks, so
+        # loss and gradients are what a single GPU would compute.  3-NN distances come from the FULL cloud.
+        from .simple_knn import distCUDA2
+        full = torch.as_tensor(np.asarray(init_points[:, :3])).float().cuda()
+        init_points, dist2 = shard_init_points(init_points, distCUDA2(full).cpu().numpy(), rank, world)
+        if opt.max_num_gaussians:
+            opt.max_num_gaussians = max(1, opt.max_num_gaussians // world)
+    gaussians.create_from_pcd(init_points[:, :3], init_points[:, 3:4], 1.0, dist2=dist2)
     scene.gaussians = gaussians
     gaussians.training_setup(opt)
     if checkpoint is not None:
@@ -183,10 +200,14 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                 gaussians.optimizer.zero_grad(set_to_none=True)
             if scene.model_path and (iteration in saving_iterations or iteration == opt.iterations):
                 log(f"[ITER {iteration}] Saving Gaussians")
-                scene.save(iteration, queryfunc)
+                if world == 1:
+                    scene.save(iteration, queryfunc)
+                else:
+                    save_sharded(scene, gaussians, iteration, queryfunc, rank)
             if scene.model_path and iteration in checkpoint_iterations:
                 log(f"[ITER {iteration}] Saving Checkpoint")
-                torch.save((gaussians.capture(), iteration), os.path.join(ckpt_dir, f"chkpnt{iteration}.pth"))
+                name = f"chkpnt{iteration}.pth" if world == 1 else f"chkpnt{iteration}_rank{rank}.pth"
+                torch.save((gaussians.capture(), iteration), os.path.join(ckpt_dir, name))
             if iteration % 100 == 0:
                 history["loss"].append((iteration, float(total)))
             if iteration in testing_iterations:
@@ -198,6 +219,23 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     history["gaussians"] = int(gaussians.get_xyz.shape[0])
     history["scene"], history["model"] = scene, gaussians
     return history
+
+
+def save_sharded(scene: Scene, gaussians: GaussianModel, iteration: int, queryfunc, rank: int):
+    """`Scene.save` for a Gaussian-sharded run: all ranks take part (the volume query is a collective), rank 0
+    writes ONE merged `point_cloud.pickle` + the volumes, in the layout `test.py` reads."""
+    import pickle
+    out = os.path.join(scene.model_path, "point_cloud/iteration_{}".format(iteration))
+    merged = gather_point_cloud(gaussians)
+    vol_pred = queryfunc(gaussians)["vol"] if queryfunc is not None else None
+    if rank != 0:
+        return
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "point_cloud.pickle"), "wb") as f:
+        pickle.dump(merged, f, pickle.HIGHEST_PROTOCOL)
+    if vol_pred is not None:
+        np.save(os.path.join(out, "vol_gt.npy"), scene.vol_gt.detach().cpu().numpy())
+        np.save(os.path.join(out, "vol_pred.npy"), vol_pred.detach().cpu().numpy())
 
 
 def _add_dataclass_args(parser, cls, skip=()):
@@ -224,6 +262,8 @@ def main(argv=None):
     ap.add_argument("--checkpoint_iterations", nargs="+", type=int, default=[])
     ap.add_argument("--start_checkpoint", type=str, default=None)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--peer_exchange", action="store_true",
+                    help="multi-GPU: sum partial images / volumes with the NVLink peer-memory kernel instead of NCCL")
     a = ap.parse_args(argv)
     pick = lambda cls: cls(**{k: getattr(a, k) for k in cls.__dataclass_fields__})
     model, pipe, opt = pick(ModelParams), pick(PipelineParams), pick(OptimizationParams)
@@ -231,12 +271,32 @@ def main(argv=None):
     if not model.model_path:
         model.model_path = os.path.join("./output", os.path.basename(model.source_path.rstrip("/")))
     os.makedirs(model.model_path, exist_ok=True)
-    with open(os.path.join(model.model_path, "cfg_args.json"), "w") as f:
-        json.dump({"model": asdict(model), "pipe": asdict(pipe), "opt": asdict(opt)}, f, indent=1)
+    if int(os.environ.get("RANK", "0")) == 0:
+        with open(os.path.join(model.model_path, "cfg_args.json"), "w") as f:
+            json.dump({"model": asdict(model), "pipe": asdict(pipe), "opt": asdict(opt)}, f, indent=1)
     random.seed(a.seed), np.random.seed(a.seed), torch.manual_seed(a.seed)     # safe_state (`general_utils.py:61-63`)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                      # launched by torchrun: one process per GPU, Gaussians sharded by index
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if a.peer_exchange:
+            from .sharded import enable_peer_exchange
+            enable_peer_exchange(True)
     hist = training(model, opt, pipe, set(a.test_iterations) | {opt.iterations}, set(a.save_iterations),
                     set(a.checkpoint_iterations), a.start_checkpoint)
     final = hist["eval"].get(opt.iterations, {})
+    if world > 1:
+        import torch.distributed as dist
+        from .sharded import enable_peer_exchange
+        enable_peer_exchange(False)
+        rank0 = dist.get_rank() == 0
+        dist.barrier()
+        dist.destroy_process_group()
+        if not rank0:
+            return
     print(json.dumps({"seconds": hist["seconds"], "ms_per_iteration": hist["seconds"] / max(hist["iterations"], 1) * 1e3,
                       "gaussians": hist["gaussians"], **final}))
 

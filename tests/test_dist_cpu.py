@@ -13,7 +13,8 @@ import torch.multiprocessing as mp
 
 import util
 from r2_gaussian_b200 import scene
-from r2_gaussian_b200.sharded import ShardedProjector, all_reduce_sum, shard_bounds
+from r2_gaussian_b200.sharded import (ShardedProjector, all_reduce_sum, gather_point_cloud, merge_point_clouds,
+                                      shard_bounds, shard_init_points)
 
 
 def _worker(rank, world, port, out_dir):
@@ -35,8 +36,22 @@ def _worker(rank, world, port, out_dir):
         x = torch.full((4,), float(rank + 1), requires_grad=True)
         y = all_reduce_sum(x * 2.0)
         (y * torch.arange(4.0)).sum().backward()
+        # sharded-training helpers: slices of the initial cloud (with the full-cloud 3-NN distances), merged export
+        rng = np.random.default_rng(0)
+        pts, d2 = rng.random((101, 4)), rng.random(101)
+        my_pts, my_d2 = shard_init_points(pts, d2, rank, world)
+        from types import SimpleNamespace
+        fake = SimpleNamespace(_xyz=torch.from_numpy(my_pts[:, :3]), _density=torch.from_numpy(my_pts[:, 3:4]),
+                               _scaling=torch.from_numpy(np.repeat(my_d2[:, None], 3, 1)),
+                               _rotation=torch.zeros(len(my_pts), 4), scale_bound=(0.001, 1.0))
+        merged = gather_point_cloud(fake)
+        assert (merged is None) == (rank != 0)
+        if rank == 0:
+            assert np.array_equal(merged["xyz"], pts[:, :3]) and np.array_equal(merged["density"], pts[:, 3:4])
+            assert np.array_equal(merged["scale"][:, 0], d2) and merged["rotation"].shape == (101, 4)
+            assert merged["scale_bound"] == (0.001, 1.0)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img.numpy(), vol=vol.numpy(), y=y.detach().numpy(),
-                 gx=x.grad.numpy())
+                 gx=x.grad.numpy(), n_pts=np.array([len(my_pts)]))
     finally:
         dist.destroy_process_group()
 
@@ -55,3 +70,14 @@ def test_sharded_sum_matches_full_render(tmp_path):
     np.testing.assert_allclose(r[0]["y"], np.full(4, 2.0 * (1 + 2)))
     for k in range(world):
         np.testing.assert_allclose(r[k]["gx"], 2.0 * np.arange(4.0))
+    assert int(r[0]["n_pts"][0]) + int(r[1]["n_pts"][0]) == 101 and int(r[0]["n_pts"][0]) == 50
+
+
+def test_merge_point_clouds_orders_by_rank():
+    a = {"xyz": np.zeros((2, 3)), "density": np.zeros((2, 1)), "scale": np.ones((2, 3)), "rotation": np.ones((2, 4)),
+         "scale_bound": None}
+    b = {k: (v + 1 if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    m = merge_point_clouds([a, b])
+    assert m["xyz"].shape == (4, 3) and m["xyz"][:2].max() == 0 and m["xyz"][2:].min() == 1 and m["scale_bound"] is None
+    with pytest.raises(ValueError):
+        merge_point_clouds([])
