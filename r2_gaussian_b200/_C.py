@@ -60,7 +60,6 @@ class _Workspace:
     Capacities are rounded to a coarse grid so that torch's caching allocator sees repeating sizes."""
 
     hints: dict = {}
-    cap_of_bytes: dict = {}   # binning buffer size in bytes -> instance capacity it was carved for
 
     @staticmethod
     def _round(n: int) -> int:
@@ -79,9 +78,22 @@ class _Workspace:
         cls.hints[key] = want if want > cur or want < cur // 2 else cur
 
 
-def _carved_capacity(binning: torch.Tensor, R: int) -> int:
+class NumRendered(int):
+    """`num_rendered` as the reference returns it (a Python int) that also remembers the instance capacity the
+    binning buffer was carved for: the backward must carve the buffer with the same number.  The autograd
+    bridges keep this object in `ctx` and hand it back unchanged, exactly like the reference's plain int."""
+
+    capacity: int
+
+    def __new__(cls, value: int, capacity: int | None = None):
+        obj = super().__new__(cls, int(value))
+        obj.capacity = int(value if capacity is None else capacity)
+        return obj
+
+
+def _carved_capacity(binning: torch.Tensor, R) -> int:
     """Instance count the binning buffer was carved for (what the backward must carve with)."""
-    return _Workspace.cap_of_bytes.get(int(binning.numel()), int(R)) if binning is not None else int(R)
+    return int(getattr(R, "capacity", R))
 
 
 def _status_pair(dev):
@@ -94,8 +106,8 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
                         debug):
     """-> (num_rendered, out_color[1,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer).
 
-    The binning buffer is provisioned for a capacity >= num_rendered (see _Workspace); the backward
-    recovers that capacity from the buffer's size."""
+    The binning buffer is provisioned for a capacity >= num_rendered (see _Workspace); num_rendered is a
+    `NumRendered` int that carries that capacity to the backward."""
     _require_cuda(means3D, "means3D")
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -123,12 +135,10 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
                 int(bool(prefiltered)), int(mode), out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(),
                 alloc.cb, None, int(bool(debug)), C.byref(nr))
             check(rc, "r2x_raster_forward")
-            return nr.value, out_color, radii, geom, alloc.tensor, img
+            return NumRendered(nr.value), out_color, radii, geom, alloc.tensor, img
         cap = _Workspace.capacity(key, P, 12)
         while True:
-            nbytes = lib.r2x_binning_bytes(cap)
-            _Workspace.cap_of_bytes[int(nbytes)] = cap
-            binning = torch.empty(nbytes, **u8)
+            binning = torch.empty(lib.r2x_binning_bytes(cap), **u8)
             rc = lib.r2x_raster_forward_async(
                 stream, P, W, H, _ptr(means3D), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
                 _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
@@ -140,7 +150,7 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
             if not overflow:
                 break
             cap = _Workspace.capacity(key, P, 12)
-    return R, out_color, radii, geom, binning, img
+    return NumRendered(R, cap), out_color, radii, geom, binning, img
 
 
 class _BinningAlloc:
@@ -231,15 +241,13 @@ def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3
             rc = lib.r2x_voxel_forward(stream, P, *grid_args, *in_args, vol.data_ptr(), _ptr(rx), _ptr(ry), _ptr(rz),
                                        geom.data_ptr(), img.data_ptr(), alloc.cb, None, int(bool(debug)), C.byref(nr))
             check(rc, "r2x_voxel_forward")
-            return nr.value, vol, rx, ry, rz, geom, alloc.tensor, img
+            return NumRendered(nr.value), vol, rx, ry, rz, geom, alloc.tensor, img
         # the instance count depends strongly on the voxel pitch: key the hint on the grid as well
         key = ("voxel", dev.index, P, nx, ny, nz, round(float(sVoxel_x) / nx, 6))
         status = _status_pair(dev)
         cap = _Workspace.capacity(key, P, 8)
         while True:
-            nbytes = lib.r2x_binning_bytes(cap)
-            _Workspace.cap_of_bytes[int(nbytes)] = cap
-            binning = torch.empty(nbytes, **u8)
+            binning = torch.empty(lib.r2x_binning_bytes(cap), **u8)
             rc = lib.r2x_voxel_forward_async(stream, P, *grid_args, *in_args, vol.data_ptr(), _ptr(rx), _ptr(ry),
                                              _ptr(rz), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
                                              status.data_ptr())
@@ -249,7 +257,7 @@ def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3
             if not overflow:
                 break
             cap = _Workspace.capacity(key, P, 8)
-    return R, vol, rx, ry, rz, geom, binning, img
+    return NumRendered(R, cap), vol, rx, ry, rz, geom, binning, img
 
 
 def voxelize_gaussians_backward(means3D, radii_x, radii_y, radii_z, scales, rotations, scale_modifier,

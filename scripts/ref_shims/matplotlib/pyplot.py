@@ -1,0 +1,5 @@
+from _absent import Absent as _A
+
+
+def __getattr__(name):
+    return _A(f"matplotlib.pyplot.{name}")

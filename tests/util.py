@@ -47,7 +47,7 @@ def to_torch(cloud, view, device="cuda", requires_grad=False):
     return t
 
 
-def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None):
+def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None, debug=False):
     import torch
     from r2_gaussian_b200 import _C
     from r2_gaussian_b200._lib import load, check
@@ -59,7 +59,8 @@ def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None):
         scales, rots, cov = empty, empty, torch.tensor(cov3D_precomp, device="cuda")
     R, color, radii, geom, binning, img = _C.rasterize_gaussians(
         t["means"], t["dens"], scales, rots, 1.0, cov, t["view"], t["proj"], view.tanfovx, view.tanfovy,
-        view.image_height, view.image_width, t["campos"], False, view.mode, False)
+        view.image_height, view.image_width, t["campos"], False, view.mode, debug)
+    t["scales_in"], t["rots_in"], t["cov_in"] = scales, rots, cov
     out = dict(R=R, image=color[0].cpu().numpy(), radii=radii.cpu().numpy(), state=(geom, binning, img), t=t)
     if export:
         lib = load()
@@ -89,7 +90,7 @@ def ours_raster_forward(cloud, view, export=True, cov3D_precomp=None):
     return out
 
 
-def ours_raster_backward(cloud, view, fwd, dL):
+def ours_raster_backward(cloud, view, fwd, dL, debug=False):
     import torch
     from r2_gaussian_b200 import _C
 
@@ -97,8 +98,8 @@ def ours_raster_backward(cloud, view, fwd, dL):
     geom, binning, img = fwd["state"]
     radii = torch.tensor(fwd["radii"], device="cuda")
     g = _C.rasterize_gaussians_backward(
-        t["means"], radii, t["scales"], t["rots"], 1.0, torch.Tensor([]), t["view"], t["proj"], view.tanfovx,
-        view.tanfovy, torch.tensor(dL, device="cuda")[None], t["campos"], geom, fwd["R"], binning, img, view.mode, False)
+        t["means"], radii, t["scales_in"], t["rots_in"], 1.0, t["cov_in"], t["view"], t["proj"], view.tanfovx,
+        view.tanfovy, torch.tensor(dL, device="cuda")[None], t["campos"], geom, fwd["R"], binning, img, view.mode, debug)
     names = ["dL_dmean2D", "dL_dopacity", "dL_dmu", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]
     return {n: x.cpu().numpy() for n, x in zip(names, g)}
 
@@ -119,15 +120,19 @@ def oracle_raster_backward(cloud, view, fwd, dL):
 
 
 # ---- voxelizer ------------------------------------------------------------------------------
-def ours_voxel_forward(cloud, nVoxel, sVoxel, center, export=True):
+def ours_voxel_forward(cloud, nVoxel, sVoxel, center, export=True, cov3D_precomp=None, debug=False):
     import torch
     from r2_gaussian_b200 import _C
     from r2_gaussian_b200._lib import load, check
 
     t = to_torch(cloud, None)
+    rots, cov = t["rots"], torch.Tensor([])
+    if cov3D_precomp is not None:   # the voxelizer needs the scales for its bounding radius either way
+        rots, cov = torch.Tensor([]), torch.tensor(cov3D_precomp, device="cuda")
+    t["rots_in"], t["cov_in"] = rots, cov
     R, vol, rx, ry, rz, geom, binning, img = _C.voxelize_gaussians(
-        t["means"], t["dens"], t["scales"], t["rots"], 1.0, torch.Tensor([]), nVoxel[0], nVoxel[1], nVoxel[2],
-        sVoxel[0], sVoxel[1], sVoxel[2], center[0], center[1], center[2], False, False)
+        t["means"], t["dens"], t["scales"], rots, 1.0, cov, nVoxel[0], nVoxel[1], nVoxel[2],
+        sVoxel[0], sVoxel[1], sVoxel[2], center[0], center[1], center[2], False, debug)
     out = dict(R=R, vol=vol.cpu().numpy(), radii_x=rx.cpu().numpy(), radii_y=ry.cpu().numpy(), radii_z=rz.cpu().numpy(),
                state=(geom, binning, img), t=t, radii_t=(rx, ry, rz))
     if export:
@@ -157,7 +162,7 @@ def ours_voxel_forward(cloud, nVoxel, sVoxel, center, export=True):
     return out
 
 
-def ours_voxel_backward(cloud, nVoxel, sVoxel, center, fwd, dL):
+def ours_voxel_backward(cloud, nVoxel, sVoxel, center, fwd, dL, debug=False):
     import torch
     from r2_gaussian_b200 import _C
 
@@ -165,9 +170,9 @@ def ours_voxel_backward(cloud, nVoxel, sVoxel, center, fwd, dL):
     geom, binning, img = fwd["state"]
     rx, ry, rz = fwd["radii_t"]
     g = _C.voxelize_gaussians_backward(
-        t["means"], rx, ry, rz, t["scales"], t["rots"], 1.0, torch.Tensor([]), torch.tensor(dL, device="cuda"), geom,
+        t["means"], rx, ry, rz, t["scales"], t["rots_in"], 1.0, t["cov_in"], torch.tensor(dL, device="cuda"), geom,
         fwd["R"], binning, img, nVoxel[0], nVoxel[1], nVoxel[2], sVoxel[0], sVoxel[1], sVoxel[2], center[0], center[1],
-        center[2], False)
+        center[2], debug)
     names = ["dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dscale", "dL_drot"]
     return {n: x.cpu().numpy() for n, x in zip(names, g)}
 
@@ -237,3 +242,106 @@ def ref_lib():
         _ref.ref_raster_forward.restype = C.c_int
         _ref.ref_voxel_forward.restype = C.c_int
     return _ref
+
+
+def need_ref():
+    """The compiled reference (oracle/_ref/libr2ref.so).  It is built in the build container (where
+    /root/reference exists) and travels to the GPU box; a GPU box without it is a broken snapshot, so
+    the parity tests FAIL there instead of skipping."""
+    import pytest
+
+    lib = ref_lib()
+    if lib is None:
+        pytest.fail("oracle/_ref/libr2ref.so is missing: run `bash oracle/build_ref.sh` in the build container "
+                    "(needs /root/reference) before sending the tree to the GPU box")
+    return lib
+
+
+def _cptr(t):
+    return C.c_void_p(t.data_cptr()) if t is not None and t.numel() else None
+
+
+def run_ref_raster(cloud, view, dL=None, cov3D_precomp=None):
+    import torch
+
+    lib = need_ref()
+    t = to_torch(cloud, view)
+    P, W, H = cloud.P, view.image_width, view.image_height
+    dev = "cuda"
+    out = torch.zeros((1, H, W), device=dev); radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    f = C.c_float
+    covp = None if cov3D_precomp is None else torch.tensor(cov3D_precomp, device=dev)
+    sc_p = None if covp is not None else _cptr(t["scales"])
+    ro_p = None if covp is not None else _cptr(t["rots"])
+    R = lib.ref_raster_forward(P, W, H, _cptr(t["means"]), _cptr(t["dens"]), sc_p, f(1.0), ro_p,
+                               _cptr(covp), _cptr(t["view"]), _cptr(t["proj"]), _cptr(t["campos"]), f(view.tanfovx),
+                               f(view.tanfovy), view.mode, _cptr(out), _cptr(radii))
+    torch.cuda.synchronize()
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    depth = torch.zeros(P, device=dev); xy = torch.zeros((P, 2), device=dev); cov = torch.zeros((P, 6), device=dev)
+    co = torch.zeros((P, 4), device=dev); mu = torch.zeros(P, device=dev)
+    tt = torch.zeros(P, dtype=torch.int32, device=dev); po = torch.zeros(P, dtype=torch.int32, device=dev)
+    ks = torch.zeros(max(R, 1), dtype=torch.int64, device=dev); pl = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+    rg = torch.zeros((T, 2), dtype=torch.int32, device=dev); nc = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    lib.ref_raster_export(P, W, H, R, _cptr(depth), _cptr(xy), _cptr(cov), _cptr(co), _cptr(mu), _cptr(tt), _cptr(po), None,
+                          None, _cptr(ks), _cptr(pl), _cptr(rg), _cptr(nc))
+    res = dict(R=R, image=out[0].cpu().numpy(), radii=radii.cpu().numpy(), depth=depth.cpu().numpy(),
+               xy=xy.cpu().numpy(), cov3D=cov.cpu().numpy(), conic_opacity=co.cpu().numpy(), mu=mu.cpu().numpy(),
+               tiles_touched=tt.cpu().numpy().astype(np.uint32), keys=ks.cpu().numpy().astype(np.uint64)[:R],
+               point_list=pl.cpu().numpy().astype(np.uint32)[:R], ranges=rg.cpu().numpy().astype(np.uint32))
+    if dL is not None:
+        z = lambda *s: torch.zeros(s, device=dev)
+        g2, gc, go, gm, g3, gcov, gs, gr = z(P, 3), z(P, 4), z(P, 1), z(P, 1), z(P, 3), z(P, 6), z(P, 3), z(P, 4)
+        dLt = torch.tensor(dL, device=dev)
+        lib.ref_raster_backward(P, R, W, H, _cptr(t["means"]), sc_p, f(1.0), ro_p, _cptr(covp),
+                                _cptr(t["view"]), _cptr(t["proj"]), _cptr(t["campos"]), f(view.tanfovx), f(view.tanfovy),
+                                _cptr(radii), _cptr(dLt), _cptr(g2), _cptr(gc), _cptr(go), _cptr(gm), _cptr(g3), _cptr(gcov),
+                                _cptr(gs), _cptr(gr), view.mode)
+        torch.cuda.synchronize()
+        res["grads"] = dict(dL_dmean2D=g2.cpu().numpy(), dL_dopacity=go.cpu().numpy(), dL_dmu=gm.cpu().numpy(),
+                            dL_dmean3D=g3.cpu().numpy(), dL_dcov3D=gcov.cpu().numpy(), dL_dscale=gs.cpu().numpy(),
+                            dL_drot=gr.cpu().numpy())
+    return res
+
+
+def run_ref_voxel(cloud, nV, sV, ctr, dL=None, cov3D_precomp=None):
+    import torch
+
+    lib = need_ref()
+    t = to_torch(cloud, None)
+    P = cloud.P
+    nx, ny, nz = nV
+    dev = "cuda"
+    f = C.c_float
+    vol = torch.zeros(nV, device=dev)
+    covp = None if cov3D_precomp is None else torch.tensor(cov3D_precomp, device=dev)
+    rx = torch.zeros(P, dtype=torch.int32, device=dev); ry = torch.zeros_like(rx); rz = torch.zeros_like(rx)
+    R = lib.ref_voxel_forward(P, nx, ny, nz, f(sV[0]), f(sV[1]), f(sV[2]), f(ctr[0]), f(ctr[1]), f(ctr[2]),
+                              _cptr(t["means"]), _cptr(t["dens"]), _cptr(t["scales"]), f(1.0),
+                              None if covp is not None else _cptr(t["rots"]), _cptr(covp),
+                              _cptr(vol), _cptr(rx), _cptr(ry), _cptr(rz))
+    torch.cuda.synchronize()
+    T = ((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8)
+    depth = torch.zeros(P, device=dev); xyz = torch.zeros((P, 3), device=dev); cov = torch.zeros((P, 6), device=dev)
+    co = torch.zeros((P, 7), device=dev)
+    tt = torch.zeros(P, dtype=torch.int32, device=dev); po = torch.zeros(P, dtype=torch.int32, device=dev)
+    ks = torch.zeros(max(R, 1), dtype=torch.int64, device=dev); pl = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+    rg = torch.zeros((T, 2), dtype=torch.int32, device=dev)
+    lib.ref_voxel_export(P, nx, ny, nz, R, _cptr(depth), _cptr(xyz), _cptr(cov), _cptr(co), _cptr(tt), _cptr(po), None, None,
+                         _cptr(ks), _cptr(pl), _cptr(rg), None)
+    res = dict(R=R, vol=vol.cpu().numpy(), radii_x=rx.cpu().numpy(), radii_y=ry.cpu().numpy(), radii_z=rz.cpu().numpy(),
+               depth=depth.cpu().numpy(), xyz_vol=xyz.cpu().numpy(), conic_opacity=co.cpu().numpy(),
+               tiles_touched=tt.cpu().numpy().astype(np.uint32), keys=ks.cpu().numpy().astype(np.uint64)[:R],
+               point_list=pl.cpu().numpy().astype(np.uint32)[:R], ranges=rg.cpu().numpy().astype(np.uint32))
+    if dL is not None:
+        z = lambda *s: torch.zeros(s, device=dev)
+        gn, gc, go, g3, gcov, gs, gr = z(P, 3), z(P, 6), z(P, 1), z(P, 3), z(P, 6), z(P, 3), z(P, 4)
+        dLt = torch.tensor(dL, device=dev)
+        lib.ref_voxel_backward(P, R, nx, ny, nz, f(sV[0]), f(sV[1]), f(sV[2]), f(ctr[0]), f(ctr[1]), f(ctr[2]),
+                               _cptr(t["means"]), _cptr(t["scales"]), f(1.0),
+                               None if covp is not None else _cptr(t["rots"]), _cptr(covp), _cptr(rx), _cptr(ry),
+                               _cptr(rz), _cptr(dLt), _cptr(gn), _cptr(gc), _cptr(go), _cptr(g3), _cptr(gcov), _cptr(gs), _cptr(gr))
+        torch.cuda.synchronize()
+        res["grads"] = dict(dL_dopacity=go.cpu().numpy(), dL_dmean3D=g3.cpu().numpy(), dL_dcov3D=gcov.cpu().numpy(),
+                            dL_dscale=gs.cpu().numpy(), dL_drot=gr.cpu().numpy())
+    return res
