@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "r2x_matcalc.cuh"
 
 #define R2X_TILE 16     // detector tile edge, pixels   (reference RAS/config.h:16-17)
 #define R2X_VTILE 8     // voxel tile edge              (reference VOX/config.h:16-18)
@@ -68,54 +69,6 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float s0, float s1, float s
     cov[3] = dot3c(M10, M10, M11, M11, M12, M12);
     cov[4] = dot3c(M20, M10, M21, M11, M22, M12);
     cov[5] = dot3c(M20, M20, M21, M21, M22, M22);
-}
-
-// Gradient of Sigma = (S R)^T (S R) w.r.t. scale (3) and the raw quaternion (4) given dL/dSigma (6,
-// off-diagonals counted once).  Plain float math (tolerance territory, not bit-exact).
-__device__ __forceinline__ void cov3d_backward(float s0, float s1, float s2, float mod, float4 q,
-                                               const float* dS6, float* dscale, float* drot) {
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    // Rc[c][k]: glm column c, row k (textual rows of the rotation matrix)
-    const float Rc[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                            {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                            {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-    const float s[3] = {mod * s0, mod * s1, mod * s2};
-    const float dS[3][3] = {{dS6[0], 0.5f * dS6[1], 0.5f * dS6[2]},
-                            {0.5f * dS6[1], dS6[3], 0.5f * dS6[4]},
-                            {0.5f * dS6[2], 0.5f * dS6[4], dS6[5]}};
-    float dMt[3][3];  // dMt[k][c] = dL/dM[c][k],  M[c][k] = s_k * Rc[c][k]
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            dMt[k][c] = (2.0f * s[k] * Rc[0][k]) * dS[c][0] + (2.0f * s[k] * Rc[1][k]) * dS[c][1] +
-                        (2.0f * s[k] * Rc[2][k]) * dS[c][2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) dscale[k] = Rc[0][k] * dMt[k][0] + Rc[1][k] * dMt[k][1] + Rc[2][k] * dMt[k][2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) dMt[k][c] *= s[k];
-    drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-    drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) -
-              4 * x * (dMt[2][2] + dMt[1][1]);
-    drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) -
-              4 * y * (dMt[2][2] + dMt[0][0]);
-    drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
-              4 * z * (dMt[1][1] + dMt[0][0]);
-}
-
-// dL/dSigma3 (6) += J^T-style pull-back of dL/dhat (6) through hat = Mm^T V Mm, Mm[c*3+r].
-__device__ __forceinline__ void dcov3d_from_dhat(const float* Mm, const float* dh, float* dcov) {
-#define M_(c, r) Mm[(c) * 3 + (r)]
-    const float da = dh[0], db = dh[1], dc = dh[2], dd = dh[3], de = dh[4], df = dh[5];
-    dcov[0] += M_(0,0)*M_(0,0)*da + M_(0,0)*M_(1,0)*db + M_(0,0)*M_(2,0)*dc + M_(1,0)*M_(1,0)*dd + M_(1,0)*M_(2,0)*de + M_(2,0)*M_(2,0)*df;
-    dcov[3] += M_(0,1)*M_(0,1)*da + M_(0,1)*M_(1,1)*db + M_(0,1)*M_(2,1)*dc + M_(1,1)*M_(1,1)*dd + M_(1,1)*M_(2,1)*de + M_(2,1)*M_(2,1)*df;
-    dcov[5] += M_(0,2)*M_(0,2)*da + M_(0,2)*M_(1,2)*db + M_(0,2)*M_(2,2)*dc + M_(1,2)*M_(1,2)*dd + M_(1,2)*M_(2,2)*de + M_(2,2)*M_(2,2)*df;
-    dcov[1] += 2*M_(0,0)*M_(0,1)*da + (M_(0,1)*M_(1,0)+M_(0,0)*M_(1,1))*db + (M_(0,1)*M_(2,0)+M_(0,0)*M_(2,1))*dc + 2*M_(1,0)*M_(1,1)*dd + (M_(1,1)*M_(2,0)+M_(1,0)*M_(2,1))*de + 2*M_(2,0)*M_(2,1)*df;
-    dcov[2] += 2*M_(0,0)*M_(0,2)*da + (M_(0,2)*M_(1,0)+M_(0,0)*M_(1,2))*db + (M_(0,2)*M_(2,0)+M_(0,0)*M_(2,2))*dc + 2*M_(1,0)*M_(1,2)*dd + (M_(1,2)*M_(2,0)+M_(1,0)*M_(2,2))*de + 2*M_(2,0)*M_(2,2)*df;
-    dcov[4] += 2*M_(0,1)*M_(0,2)*da + (M_(0,2)*M_(1,1)+M_(0,1)*M_(1,2))*db + (M_(0,2)*M_(2,1)+M_(0,1)*M_(2,2))*dc + 2*M_(1,1)*M_(1,2)*dd + (M_(1,2)*M_(2,1)+M_(1,1)*M_(2,2))*de + 2*M_(2,1)*M_(2,2)*df;
-#undef M_
 }
 
 // ---------------------------------------------------------------------------------------------

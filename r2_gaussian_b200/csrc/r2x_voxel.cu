@@ -507,20 +507,19 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
         dmean[2] = rho * (-inv[5] * Sz - inv[2] * Sx - inv[4] * Sy) * vg.dvz;
         const float ga = -0.5f * rho * Sxx, gb = -rho * Sxy, gc = -rho * Sxz, gd = -0.5f * rho * Syy, ge = -rho * Syz,
                     gf = -0.5f * rho * Szz;
-        const float a = vc.a, b = vc.b, c = vc.c, d = vc.d, e = vc.e, f = vc.f;
-        const float denom = a * d * f + 2 * b * c * e - a * e * e - f * b * b - d * c * c;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        if (denom2inv != 0.f) {
-            const float n_da = d * f - e * e, n_db = 2 * c * e - 2 * f * b, n_dc = 2 * b * e - 2 * d * c;
-            const float n_dd = a * f - c * c, n_de = 2 * b * c - 2 * a * e, n_df = a * d - b * b;
-            const float ce_bf = c * e - b * f, be_cd = b * e - c * d, bc_ae = b * c - a * e;
+        // conic3D = Sv^-1 (Sv = voxel-space covariance):  dL/dSv = -adj(Sv) G adj(Sv) / det^2, with the reference's
+        // regularised 1 / (det^2 + 1e-7) (VOX/backward.cu:132-168); then Sv = D Sigma D, D = diag(1/dVoxel).
+        const float sv[6] = {vc.a, vc.b, vc.c, vc.d, vc.e, vc.f};
+        Mat3 K;
+        const float det = sym_cofactors(sv, K);
+        const float inv_det_sq = 1.0f / (det * det + 0.0000001f);
+        if (inv_det_sq != 0.f) {
+            const float g6[6] = {ga, gb, gc, gd, ge, gf};
+            const Mat3 T = matmul<false, false>(K, matmul<false, false>(sym_grad_full(g6), K));
             float dh[6];
-            dh[0] = denom2inv * (-n_da*n_da*ga - ce_bf*n_da*gb - be_cd*n_da*gc + (f*denom-n_dd*n_da)*gd + (-e*denom-bc_ae*n_da)*ge + (d*denom-n_df*n_da)*gf);
-            dh[1] = denom2inv * (-n_da*n_db*ga + (-f*denom-ce_bf*n_db)*gb + (e*denom-be_cd*n_db)*gc - n_dd*n_db*gd + (c*denom-bc_ae*n_db)*ge + (-2*b*denom-n_df*n_db)*gf);
-            dh[2] = denom2inv * (-n_da*n_dc*ga + (e*denom-ce_bf*n_dc)*gb + (-d*denom-be_cd*n_dc)*gc + (-2*c*denom-n_dd*n_dc)*gd + (b*denom-bc_ae*n_dc)*ge - n_df*n_dc*gf);
-            dh[3] = denom2inv * ((f*denom-n_da*n_dd)*ga - ce_bf*n_dd*gb + (-c*denom-be_cd*n_dd)*gc - n_dd*n_dd*gd - bc_ae*n_dd*ge + (a*denom-n_df*n_dd)*gf);
-            dh[4] = denom2inv * ((-2*e*denom-n_da*n_de)*ga + (c*denom-ce_bf*n_de)*gb + (b*denom-be_cd*n_de)*gc - n_dd*n_de*gd + (-a*denom-bc_ae*n_de)*ge + -n_df*n_de*gf);
-            dh[5] = denom2inv * ((d*denom-n_da*n_df)*ga + (-b*denom-ce_bf*n_df)*gb - be_cd*n_df*gc + (a*denom-n_dd*n_df)*gd - bc_ae*n_df*ge - n_df*n_df*gf);
+            sym_grad_pack(T, dh);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dh[k] *= -inv_det_sq;
             const float Mm[9] = {vg.ix, 0.f, 0.f, 0.f, vg.iy, 0.f, 0.f, 0.f, vg.iz};
             dcov3d_from_dhat(Mm, dh, dcov);
         }
