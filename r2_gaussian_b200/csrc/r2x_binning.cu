@@ -1,11 +1,22 @@
 // r2x_binning.cu -- see r2x_binning.cuh for the design.
+#include <cstdlib>
 #include "r2x_binning.cuh"
 
 namespace r2x {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t plan_items(long long R) { return (size_t)(R > 0 ? R : 1) / PLAN_CHUNK + 1; }
+static size_t plan_items(long long R) { return (size_t)(R > 0 ? R : 1) / PLAN_MIN_CHUNK + 1; }
+
+int plan_chunk_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("R2X_CHUNK");
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 
 size_t binning_bytes(long long R) {
     size_t r = (size_t)(R > 0 ? R : 1);
@@ -51,6 +62,7 @@ TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
     pl.extra_item = bv.extra_item;
     pl.partial = bv.partial;
     pl.num_tiles = num_tiles;
+    pl.chunk_override = plan_chunk_override();
     pl.max_extra = (long long)plan_items(bv.capacity);
     return pl;
 }
@@ -60,8 +72,19 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     __shared__ uint32_t s_carry;
     const int T = pl.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the lists are contiguous and tile-major: the last non-empty tile ends at R
+    uint32_t Rloc = 0;
+    for (int t = tid; t < T; t += 1024) Rloc = max(Rloc, ranges[t].y);
+    Rloc = __reduce_max_sync(0xffffffffu, Rloc);
     if (tid == 0) s_carry = 0;
-    if (tid < 4) pl.counter[tid] = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&s_carry, Rloc);
+    __syncthreads();
+    const uint32_t C = plan_chunk_for(s_carry, pl.chunk_override);
+    __syncthreads();
+    if (tid == 0) s_carry = 0;
+    if (tid < 2) pl.counter[tid] = 0;
+    if (tid == 2) pl.counter[2] = C;
     __syncthreads();
     for (int base = 0; base < T; base += 1024) {
         const int t = base + tid;
@@ -69,7 +92,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
         if (t < T) {
             const uint2 r = ranges[t];
             const uint32_t n = r.y - r.x;
-            a = n ? (n - 1) / PLAN_CHUNK : 0u;  // extra chunks beyond the first
+            a = n ? (n - 1) / C : 0u;  // extra chunks beyond the first
 #pragma unroll
             for (int k = 0; k < PLAN_DONE_SLOTS; ++k) pl.tile_done[(size_t)t * PLAN_DONE_SLOTS + k] = 0;
         }
@@ -629,7 +652,7 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
                                                                    uint2* __restrict__ ranges, TilePlan pl,
                                                                    uint32_t* __restrict__ point_list,
                                                                    uint32_t* __restrict__ inst_pos, long long capacity,
-                                                                   int gx, int gy) {
+                                                                   int gx, int gy, const uint32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_w[8];
     const int T = db.num_tiles;
@@ -667,13 +690,14 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so EMPTY ranges are
     // published -- the render then produces zeros without touching unwritten list entries -- and the host sees
     // status[1] = 1 (direct_scan) and re-runs with a larger buffer.
+    const uint32_t C = plan_chunk_for(status[0], pl.chunk_override);   // status[0] = R (direct_scan)
     const int npub = db.nb < DIRECT_BLOCK ? db.nb : DIRECT_BLOCK;
     const bool pub = (b < npub) && (tid % npub == b);
     const unsigned long long tot = cta_exclusive_scan_1pass<unsigned long long>(
         T,
         [&](int i) {
             const uint32_t c = tc[i];
-            return ((unsigned long long)(c ? (c - 1) / PLAN_CHUNK : 0u) << 32) | c;
+            return ((unsigned long long)(c ? (c - 1) / C : 0u) << 32) | c;
         },
         [&](int i, unsigned long long ex64, unsigned long long v64, unsigned long long total) {
             const uint32_t ex = (uint32_t)ex64, cnt = (uint32_t)v64;
@@ -693,7 +717,8 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     const uint32_t R = (uint32_t)tot;
     if (b == 0 && tid == 0) {
         pl.extra_off[T] = ((long long)R > capacity) ? 0u : (uint32_t)(tot >> 32);
-        pl.counter[0] = pl.counter[1] = pl.counter[2] = pl.counter[3] = 0;
+        pl.counter[0] = pl.counter[1] = pl.counter[3] = 0;
+        pl.counter[2] = C;
     }
     uint32_t wpre = 0;
 #pragma unroll
@@ -743,13 +768,13 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
 
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
                        const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
-                       int gy) {
+                       int gy, const uint32_t* status) {
     const size_t smem = (size_t)db.num_tiles * 36;
     if (smem > 40 * 1024)
         R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          DIRECT_MAX_TILES * 36));
     direct_fill_kernel<<<db.nb, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
-                                                              bv.point_list, bv.inst_pos, bv.capacity, gx, gy);
+                                                              bv.point_list, bv.inst_pos, bv.capacity, gx, gy, status);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
