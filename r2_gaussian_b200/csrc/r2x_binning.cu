@@ -557,6 +557,7 @@ __device__ __forceinline__ V cta_exclusive_scan_1pass(int n, Load load, Store st
 constexpr int SCAN_SEGS = 32;
 __global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_t* __restrict__ status,
                                                            long long capacity, uint32_t* __restrict__ status_out) {
+    pdl_prologue();
     __shared__ uint32_t s_seg[SCAN_SEGS][33];
     __shared__ uint32_t s_red[32];
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
@@ -634,18 +635,23 @@ __global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_
 
 int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, long long capacity,
                        uint32_t* status_out) {
-    direct_scan_kernel<<<(db.num_tiles + 31) / 32, 1024, 0, st>>>(db, status, capacity, status_out);
+    R2X_CUDA_OK(pdl_launch(direct_scan_kernel, dim3((db.num_tiles + 31) / 32), dim3(1024), 0, st, db, status, capacity,
+                           status_out));
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// CTA b places the instances of Gaussians [256 b, 256 b + 256).  It marks, per tile, WHICH of its Gaussians
-// touch the tile (a 256-bit mask per tile, word w = warp w's 32 Gaussians); a thread per tile then walks the
-// set bits in ascending order = ascending Gaussian id, which is the stable order, and writes the ids to
-// range[t].x + prefix[b][t] + k.  No search, no division per instance, no warp match.  Every CTA derives the
-// tile ranges and its instance base itself (exclusive scans of tile_count / block_total: small and L2-hot),
-// so nothing serial sits between the column scan and this kernel; the publication of the ranges and of the
-// work plan for the render is spread over the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32.
+// CTA b places the instances of Gaussians [256 b, 256 b + 256).  It marks, per tile, WHICH of its Gaussians touch
+// the tile (a 256-bit mask per tile, word w = warp w's 32 Gaussians, one ATOMS.OR per instance), turns the word
+// populations into per-word ranks, and then every thread walks the tiles of ITS OWN Gaussian again (lane per
+// instance, the same loop as the marking) and writes the Gaussian id to
+//     range[t].x + prefix[b][t] + rank of the Gaussian among the CTA's Gaussians on tile t
+//                                 = wrank[w][t] + popc(mask[w][t] & lanes below)
+// => every tile list is ascending in Gaussian id (the stable order) without any search, sort or warp match, and the
+// instance's emission-order slot (backward moments) is a running counter.  Every CTA derives the tile ranges and its
+// instance base itself (exclusive scans of tile_count / block_total: small and L2-hot), so nothing serial sits between
+// the column scan and this kernel; the publication of the ranges and of the work plan for the render is spread over
+// the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32 | wrank[8][T] u8.
 __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const uint16_t* __restrict__ cube,
                                                                    const uint32_t* __restrict__ tiles_touched,
                                                                    uint32_t* __restrict__ offsets, DirectBin db,
@@ -653,14 +659,15 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
                                                                    uint32_t* __restrict__ point_list,
                                                                    uint32_t* __restrict__ inst_pos, long long capacity,
                                                                    int gx, int gy, const uint32_t* __restrict__ status) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_w[8];
     const int T = db.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tc = db.tile_count;
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);   // [8][T]
-    uint32_t* s_base = s_mask + 8 * (size_t)T;                   // [T]
-    __shared__ uint2 s_aw[DIRECT_BLOCK];   // per Gaussian: (slot of its first instance - index of its first tile, w | h << 16)
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);                    // [8][T]
+    uint32_t* s_base = s_mask + 8 * (size_t)T;                                    // [T]
+    unsigned char* s_wrank = reinterpret_cast<unsigned char*>(s_base + T);        // [8][T]
     __shared__ uint32_t s_w8[8];
 
     const int b = blockIdx.x;
@@ -727,54 +734,57 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     const uint32_t lex = wpre + ia - n;
     if (g < P) offsets[g] = bbase + lex + n;     // inclusive scan, same meaning as the reference's point_offsets
     if ((long long)R > capacity) return;         // overflow: nothing may be written (uniform across the grid)
+    const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff, z1 = c45 >> 16;
     // mark
-    if (n) {
-        const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff,
-                       z1 = c45 >> 16;
-        // emission slot of instance (tx,ty,tz) = bbase + lex + ((tz-z0) h + (ty-y0)) w + (tx-x0)
-        //                                      = [bbase + lex - ((z0 h + y0) w + x0)] + (tz h + ty) w + tx   (mod 2^32)
-        const uint32_t w = x1 - x0, h = y1 - y0;
-        s_aw[tid] = make_uint2(bbase + lex - ((z0 * h + y0) * w + x0), w | (h << 16));
+    {
         uint32_t* plane = s_mask + (size_t)warp * T;
         const uint32_t bit = 1u << lane;
+        if (n)
+            for (uint32_t z = z0; z < z1; ++z)
+                for (uint32_t y = y0; y < y1; ++y) {
+                    const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
+                    for (uint32_t x = x0; x < x1; ++x) atomicOr(&plane[rowb + x], bit);
+                }
+    }
+    __syncthreads();
+    // rank of word w inside its tile's run = population of the words below it
+    for (int t = tid; t < T; t += DIRECT_BLOCK) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            s_wrank[(size_t)w * T + t] = (unsigned char)run;    // <= 224
+            run += __popc(s_mask[(size_t)w * T + t]);
+        }
+    }
+    __syncthreads();
+    // place: lane per instance, tiles of this thread's Gaussian in emission order (z, y, x ascending)
+    if (n) {
+        const uint32_t* plane = s_mask + (size_t)warp * T;
+        const unsigned char* wr = s_wrank + (size_t)warp * T;
+        const uint32_t below = (1u << lane) - 1u;
+        uint32_t slot = bbase + lex;
         for (uint32_t z = z0; z < z1; ++z)
             for (uint32_t y = y0; y < y1; ++y) {
                 const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
-                for (uint32_t x = x0; x < x1; ++x) atomicOr(&plane[rowb + x], bit);
+                for (uint32_t x = x0; x < x1; ++x) {
+                    const uint32_t t = rowb + x;
+                    const uint32_t pos = s_base[t] + wr[t] + __popc(plane[t] & below);
+                    point_list[pos] = (uint32_t)g;
+                    inst_pos[pos] = slot++;
+                }
             }
-    }
-    __syncthreads();
-    // place
-    const uint32_t gxy = (uint32_t)gx * (uint32_t)gy;
-    for (int t = tid; t < T; t += DIRECT_BLOCK) {
-        uint32_t pos = s_base[t];
-        const uint32_t tz = (uint32_t)t / gxy, rem = (uint32_t)t - tz * gxy, ty = rem / (uint32_t)gx,
-                       tx = rem - ty * (uint32_t)gx;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            uint32_t m = s_mask[(size_t)w * T + t];
-            while (m) {
-                const int bitpos = __ffs(m) - 1;
-                m &= m - 1;
-                const int gl = w * 32 + bitpos;
-                const uint2 aw = s_aw[gl];
-                point_list[pos] = (uint32_t)(b * DIRECT_BLOCK + gl);
-                inst_pos[pos] = aw.x + (tz * (aw.y >> 16) + ty) * (aw.y & 0xffffu) + tx;
-                ++pos;
-            }
-        }
     }
 }
 
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
                        const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
                        int gy, const uint32_t* status) {
-    const size_t smem = (size_t)db.num_tiles * 36;
+    const size_t smem = (size_t)db.num_tiles * 44;
     if (smem > 40 * 1024)
         R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DIRECT_MAX_TILES * 36));
-    direct_fill_kernel<<<db.nb, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
-                                                              bv.point_list, bv.inst_pos, bv.capacity, gx, gy, status);
+                                         DIRECT_MAX_TILES * 44));
+    R2X_CUDA_OK(pdl_launch(direct_fill_kernel, dim3(db.nb), dim3(DIRECT_BLOCK), smem, st, P, cube, tiles_touched, offsets,
+                           db, ranges, plan, bv.point_list, bv.inst_pos, bv.capacity, gx, gy, status));
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
