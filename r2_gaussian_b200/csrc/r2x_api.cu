@@ -171,7 +171,7 @@ __global__ void voxel_export_geom_kernel(int P, VoxelGeom geom, float* means3D_n
     if (means3D_norm) {
         means3D_norm[3 * (size_t)g] = r0.x; means3D_norm[3 * (size_t)g + 1] = r0.y; means3D_norm[3 * (size_t)g + 2] = r0.z;
     }
-    if (depths) depths[g] = r2.z;
+    if (depths) depths[g] = geom.rec[4 * (size_t)g + 3].y;
     if (conic_opacity) {
         const float L = 1.4426950408889634f;
         float* co = conic_opacity + 7 * (size_t)g;
@@ -559,10 +559,10 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok((int)tiles)) {
             export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
-                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
+                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 13, 16, keys, point_list);
         } else {
             const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
-            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 13, 16, keys, point_list);
         }
     }
     R2X_CUDA_OK(cudaGetLastError());
