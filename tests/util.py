@@ -258,7 +258,7 @@ def need_ref():
 
 
 def _cptr(t):
-    return C.c_void_p(t.data_cptr()) if t is not None and t.numel() else None
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
 
 
 def run_ref_raster(cloud, view, dL=None, cov3D_precomp=None):
