@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--cloud", default="init", choices=["init", "trained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` block (other BASELINE configs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the `parity` block (timed views vs the reference's kernels)")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank partial images are summed (NVLink peer-memory kernel | NCCL)")
     return ap.parse_args()
@@ -219,6 +221,55 @@ def cpu_baseline_torch(cloud, views, n_proj=3):
             "sample": f"{n_proj} full projections of the same scene after one warm-up projection"}
 
 
+def parity_vs_reference(render_view, cloud, views, dev, W, H, which=(0, 17, 34)):
+    """The image (and radii, when `render_view` returns them for the whole cloud) of three of the timed views against
+    the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libr2ref.so) run on the same inputs on this GPU.
+    render_view(i) -> (image [1,H,W] device tensor, radii int32[P] device tensor or None)."""
+    import torch
+
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libr2ref.so")
+    if not os.path.exists(ref_path):
+        return {"unavailable": "oracle/_ref/libr2ref.so not present"}
+    lib = C.CDLL(ref_path)
+    lib.ref_raster_forward.restype = C.c_int
+    P = cloud.P
+    means = torch.tensor(cloud.means, device=dev); scales = torch.tensor(cloud.scales, device=dev)
+    rots = torch.tensor(cloud.rotations, device=dev); dens = torch.tensor(cloud.density, device=dev)
+    dv = device_views(views, dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    f = C.c_float
+    res = {"views": [], "max_abs": 0.0, "max_rel_to_max": 0.0, "radii_equal": True, "num_rendered_equal": None,
+           "bar": "|ours - ref| <= 1e-5 * max|ref| + 1e-7; radii bit-exact",
+           "reference": "oracle/_ref/libr2ref.so (the reference's RAS/*.cu, unmodified) on the same GPU"}
+    rel_all = []
+    for i in which:
+        i = i % len(dv)
+        v = dv[i]
+        out = torch.zeros((1, H, W), device=dev); radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        lib.ref_raster_forward(P, W, H, vp(means), vp(dens), vp(scales), f(1.0), vp(rots), None, vp(v["view"]),
+                               vp(v["proj"]), vp(v["campos"]), f(v["tx"]), f(v["ty"]), int(v["mode"]), vp(out), vp(radii))
+        torch.cuda.synchronize(dev)
+        img, my_radii = render_view(i)
+        torch.cuda.synchronize(dev)
+        diff = (img.double() - out.double()).abs()
+        scale = float(out.abs().max())
+        res["views"].append(int(i))
+        res["max_abs"] = max(res["max_abs"], float(diff.max()))
+        res["max_rel_to_max"] = max(res["max_rel_to_max"], float(diff.max()) / max(scale, 1e-30))
+        if my_radii is not None:
+            res["radii_equal"] = bool(res["radii_equal"] and torch.equal(my_radii, radii))
+        nz = out.abs() > 1e-3 * scale            # per-pixel relative error where the signal is not negligible
+        rel_all.append((diff[nz] / out.double().abs()[nz]).flatten())
+    rel = torch.cat(rel_all)
+    if rel.numel():
+        q = torch.quantile(rel[:: max(1, rel.numel() // 1_000_000)], torch.tensor([0.5, 0.99, 0.9999], dtype=rel.dtype, device=rel.device))
+        res["per_pixel_rel_err"] = {"median": float(q[0]), "p99": float(q[1]), "p99.99": float(q[2]), "max": float(rel.max()),
+                                    "over": "pixels with |ref| > 1e-3 max|ref|"}
+    res["pass"] = bool(res["max_rel_to_max"] <= 1e-5 + 1e-7 / max(scale, 1e-30) and res["radii_equal"])
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -353,8 +404,9 @@ def run_ours(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_render * 1e3, "peak_source": peak_src,
                 "pair_evals_per_launch": pairs, "pair_evals_per_s": pairs / t_render,
-                "note": "kernel is MUFU/FP32-issue-bound (8 issue slots incl. 1 MUFU.EX2 per pixel-Gaussian "
-                        "pair), not HBM-bound; see DESIGN.md section 5"}
+                "timed": "r2x_raster_render_only = plan_kernel (queue reset, a few us) + raster_render_kernel, CUDA events, L2 flushed",
+                "note": "kernel is FP32-issue-bound (multiplicative forward differences: ~5 issue slots and 0.5 "
+                        "MUFU.EX2 per pixel-Gaussian pair), not HBM-bound; see DESIGN.md section 5"}
     try:   # the bound that does apply: one MUFU.EX2 per pair; 15.85 ex2/clk/SM measured (scripts/micro/mufu_rate.cu)
         props = torch.cuda.get_device_properties(dev)
         mhz = float(sampler.summary().get("sm_mhz") or 0.0) or 1965.0
@@ -363,6 +415,28 @@ def run_ours(args, rank, world, local_rank):
                             "peak_source": f"15.85 ex2/clk/SM (measured) x {props.multi_processor_count} SMs x {mhz:.0f} MHz"}
     except Exception as e:   # informational only
         roofline["mufu"] = {"error": str(e)}
+
+    # ---- parity of the timed path against the reference's own kernels (rank 0; N > 1: the summed image) ----
+    parity = None
+    if not args.no_parity:
+        which = (0, 17, 34)
+        if world == 1:
+            parity = parity_vs_reference(lambda i: (fwd(i).clone(), eng.radii.clone()), cloud, views, dev, W, H, which)
+        else:
+            imgs = []
+            for i in which:                 # every rank takes part in the exchange
+                if reducer is not None:
+                    step(i)
+                    imgs.append(final.clone())
+                else:
+                    o = fwd(i)
+                    dist.all_reduce(o, op=dist.ReduceOp.SUM)
+                    imgs.append(o.clone())
+            sync()
+            if rank == 0:
+                it = iter(imgs)
+                parity = parity_vs_reference(lambda i: (next(it), None), cloud, views, dev, W, H, which)
+            sync()
 
     result = {
         "metric": METRIC, "value": args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -381,6 +455,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "clocks": sampler.summary(),
     }
+    if parity is not None:
+        result["parity"] = parity
 
     # ---- e2e: host buffers in, host image out, through the public API ----
     if not args.no_e2e:
@@ -452,6 +528,12 @@ def run_ours(args, rank, world, local_rank):
                           "summed over ranks on the device, pinned host inputs, image read back each step")
         result["e2e"] = e2e
 
+    if rank == 0 and world == 1 and not args.no_secondary:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import secondary
+        del eng
+        torch.cuda.empty_cache()
+        result["secondary"] = secondary.measure(dev, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cloud, views, 2)
         result["cpu_baseline_torch"] = cpu_baseline_torch(cloud, views, 3)

@@ -197,7 +197,9 @@ int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, doubl
  * r2x_ipc_open), and r2x_peer_allreduce_sum signals, waits and adds the `world` partial buffers in rank order
  * (bitwise identical result on every rank).  bufs[p] / flags[p]: rank p's partial buffer (n floats) and flag
  * array (R2X_MAX_PEERS uint32, zero-initialised) as mapped in THIS process; `epoch` increases by one per call;
- * callers double-buffer the partial buffers by epoch parity.  status_dev[0] is set to 1 if a peer never arrived. */
+ * callers double-buffer the partial buffers by epoch parity.  status_dev[0] is set to 1 if a peer never arrived
+ * within the time-out (~2 s; r2x_peer_allreduce_sum_t takes it in SM clock cycles) -- the sum is then invalid and
+ * the caller must check the status word at its next synchronisation point (sharded.check_peer_exchange). */
 #define R2X_MAX_PEERS 16
 int r2x_peer_alloc(size_t bytes, void** dev_ptr);
 int r2x_peer_free(void* dev_ptr);
@@ -206,6 +208,8 @@ int r2x_ipc_open(const unsigned char* handle64, void** dev_ptr);
 int r2x_ipc_close(void* dev_ptr);
 int r2x_peer_allreduce_sum(void* stream, int world, int rank, const float* const* bufs, uint32_t* const* flags,
                            uint32_t epoch, float* out, long long n, uint32_t* status_dev);
+int r2x_peer_allreduce_sum_t(void* stream, int world, int rank, const float* const* bufs, uint32_t* const* flags,
+                             uint32_t epoch, float* out, long long n, uint32_t* status_dev, long long timeout_cycles);
 
 #ifdef __cplusplus
 }

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "r2x_ipc_open": (_i, [_vp, C.POINTER(_vp)]),
     "r2x_ipc_close": (_i, [_vp]),
     "r2x_peer_allreduce_sum": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp]),
+    "r2x_peer_allreduce_sum_t": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp, _ll]),
 }
 
 

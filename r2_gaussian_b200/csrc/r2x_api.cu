@@ -49,7 +49,7 @@ struct RasterState {
 
 size_t raster_geom_bytes(int P) {
     size_t p = (size_t)(P > 0 ? P : 1);
-    return al(p * 32) + al(p * 16) + al(p * 12) + 3 * al(p * 4) + al(scan_state_bytes((int)p)) + al(16) + 512;
+    return al(p * 32) + al(p * 16) + al(p * 12) + 4 * al(p * 4) + al(scan_state_bytes((int)p)) + al(16) + 512;
 }
 RasterState carve_raster(const void* buf, int P, int W, int H) {
     size_t p = (size_t)(P > 0 ? P : 1);
@@ -58,6 +58,7 @@ RasterState carve_raster(const void* buf, int P, int W, int H) {
     s.geom.rec = c.take<float4>(2 * p);
     s.geom.aux = c.take<float4>(p);
     s.geom.depth = c.take<float>(p);
+    s.geom.mu = c.take<float>(p);
     s.geom.cube = c.take<uint16_t>(6 * p);
     s.geom.tiles_touched = c.take<uint32_t>(p);
     s.geom.offsets = c.take<uint32_t>(p);
@@ -158,7 +159,7 @@ __global__ void raster_export_geom_kernel(int P, RasterGeom geom, float* means2D
         conic_opacity[4 * (size_t)g] = a.x; conic_opacity[4 * (size_t)g + 1] = a.y;
         conic_opacity[4 * (size_t)g + 2] = a.z; conic_opacity[4 * (size_t)g + 3] = a.w;
     }
-    if (mus) mus[g] = r1.w;
+    if (mus) mus[g] = geom.mu[g];
     if (tiles_touched) tiles_touched[g] = geom.tiles_touched[g];
     if (point_offsets) point_offsets[g] = geom.offsets[g];
 }
@@ -170,7 +171,7 @@ __global__ void voxel_export_geom_kernel(int P, VoxelGeom geom, float* means3D_n
     if (means3D_norm) {
         means3D_norm[3 * (size_t)g] = r0.x; means3D_norm[3 * (size_t)g + 1] = r0.y; means3D_norm[3 * (size_t)g + 2] = r0.z;
     }
-    if (depths) depths[g] = r2.z;
+    if (depths) depths[g] = geom.rec[4 * (size_t)g + 3].y;
     if (conic_opacity) {
         const float L = 1.4426950408889634f;
         float* co = conic_opacity + 7 * (size_t)g;
@@ -264,7 +265,7 @@ int raster_forward_impl(cudaStream_t st, int P, int W, int H, const float* means
     const TilePlan plan = carve_plan(image_buf, tiles, bv);
     if (direct) {
         R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv,
-                                   s.geom.gx, s.geom.gy));
+                                   s.geom.gx, s.geom.gy, s.status));
     } else {
         status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
         R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, s.geom.gx, s.geom.gy, tiles,
@@ -340,7 +341,7 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
     const TilePlan plan = carve_plan(image_buf, tiles, bv);
     if (direct) {
         R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv, vg.gx,
-                                   vg.gy));
+                                   vg.gy, s.status));
     } else {
         status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
         R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, vg.gx, vg.gy, tiles, s.status,
@@ -558,10 +559,10 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok((int)tiles)) {
             export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
-                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
+                R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 13, 16, keys, point_list);
         } else {
             const uint32_t* sorted = bv.keys[sort_passes((int)tiles) & 1];
-            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 10, 16, keys, point_list);
+            export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, s.status, sorted, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 13, 16, keys, point_list);
         }
     }
     R2X_CUDA_OK(cudaGetLastError());

@@ -1,11 +1,22 @@
 // r2x_binning.cu -- see r2x_binning.cuh for the design.
+#include <cstdlib>
 #include "r2x_binning.cuh"
 
 namespace r2x {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t plan_items(long long R) { return (size_t)(R > 0 ? R : 1) / PLAN_CHUNK + 1; }
+static size_t plan_items(long long R) { return (size_t)(R > 0 ? R : 1) / PLAN_MIN_CHUNK + 1; }
+
+int plan_chunk_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("R2X_CHUNK");
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 
 size_t binning_bytes(long long R) {
     size_t r = (size_t)(R > 0 ? R : 1);
@@ -51,6 +62,7 @@ TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
     pl.extra_item = bv.extra_item;
     pl.partial = bv.partial;
     pl.num_tiles = num_tiles;
+    pl.chunk_override = plan_chunk_override();
     pl.max_extra = (long long)plan_items(bv.capacity);
     return pl;
 }
@@ -60,8 +72,19 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     __shared__ uint32_t s_carry;
     const int T = pl.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the lists are contiguous and tile-major: the last non-empty tile ends at R
+    uint32_t Rloc = 0;
+    for (int t = tid; t < T; t += 1024) Rloc = max(Rloc, ranges[t].y);
+    Rloc = __reduce_max_sync(0xffffffffu, Rloc);
     if (tid == 0) s_carry = 0;
-    if (tid < 4) pl.counter[tid] = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&s_carry, Rloc);
+    __syncthreads();
+    const uint32_t C = plan_chunk_for(s_carry, pl.chunk_override);
+    __syncthreads();
+    if (tid == 0) s_carry = 0;
+    if (tid < 2) pl.counter[tid] = 0;
+    if (tid == 2) pl.counter[2] = C;
     __syncthreads();
     for (int base = 0; base < T; base += 1024) {
         const int t = base + tid;
@@ -69,7 +92,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
         if (t < T) {
             const uint2 r = ranges[t];
             const uint32_t n = r.y - r.x;
-            a = n ? (n - 1) / PLAN_CHUNK : 0u;  // extra chunks beyond the first
+            a = n ? (n - 1) / C : 0u;  // extra chunks beyond the first
 #pragma unroll
             for (int k = 0; k < PLAN_DONE_SLOTS; ++k) pl.tile_done[(size_t)t * PLAN_DONE_SLOTS + k] = 0;
         }
@@ -534,6 +557,7 @@ __device__ __forceinline__ V cta_exclusive_scan_1pass(int n, Load load, Store st
 constexpr int SCAN_SEGS = 32;
 __global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_t* __restrict__ status,
                                                            long long capacity, uint32_t* __restrict__ status_out) {
+    pdl_prologue();
     __shared__ uint32_t s_seg[SCAN_SEGS][33];
     __shared__ uint32_t s_red[32];
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
@@ -611,33 +635,39 @@ __global__ void __launch_bounds__(1024) direct_scan_kernel(DirectBin db, uint32_
 
 int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, long long capacity,
                        uint32_t* status_out) {
-    direct_scan_kernel<<<(db.num_tiles + 31) / 32, 1024, 0, st>>>(db, status, capacity, status_out);
+    R2X_CUDA_OK(pdl_launch(direct_scan_kernel, dim3((db.num_tiles + 31) / 32), dim3(1024), 0, st, db, status, capacity,
+                           status_out));
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// CTA b places the instances of Gaussians [256 b, 256 b + 256).  It marks, per tile, WHICH of its Gaussians
-// touch the tile (a 256-bit mask per tile, word w = warp w's 32 Gaussians); a thread per tile then walks the
-// set bits in ascending order = ascending Gaussian id, which is the stable order, and writes the ids to
-// range[t].x + prefix[b][t] + k.  No search, no division per instance, no warp match.  Every CTA derives the
-// tile ranges and its instance base itself (exclusive scans of tile_count / block_total: small and L2-hot),
-// so nothing serial sits between the column scan and this kernel; the publication of the ranges and of the
-// work plan for the render is spread over the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32.
+// CTA b places the instances of Gaussians [256 b, 256 b + 256).  It marks, per tile, WHICH of its Gaussians touch
+// the tile (a 256-bit mask per tile, word w = warp w's 32 Gaussians, one ATOMS.OR per instance), turns the word
+// populations into per-word ranks, and then every thread walks the tiles of ITS OWN Gaussian again (lane per
+// instance, the same loop as the marking) and writes the Gaussian id to
+//     range[t].x + prefix[b][t] + rank of the Gaussian among the CTA's Gaussians on tile t
+//                                 = wrank[w][t] + popc(mask[w][t] & lanes below)
+// => every tile list is ascending in Gaussian id (the stable order) without any search, sort or warp match, and the
+// instance's emission-order slot (backward moments) is a running counter.  Every CTA derives the tile ranges and its
+// instance base itself (exclusive scans of tile_count / block_total: small and L2-hot), so nothing serial sits between
+// the column scan and this kernel; the publication of the ranges and of the work plan for the render is spread over
+// the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32 | wrank[8][T] u8.
 __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const uint16_t* __restrict__ cube,
                                                                    const uint32_t* __restrict__ tiles_touched,
                                                                    uint32_t* __restrict__ offsets, DirectBin db,
                                                                    uint2* __restrict__ ranges, TilePlan pl,
                                                                    uint32_t* __restrict__ point_list,
                                                                    uint32_t* __restrict__ inst_pos, long long capacity,
-                                                                   int gx, int gy) {
+                                                                   int gx, int gy, const uint32_t* __restrict__ status) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_w[8];
     const int T = db.num_tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tc = db.tile_count;
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);   // [8][T]
-    uint32_t* s_base = s_mask + 8 * (size_t)T;                   // [T]
-    __shared__ uint2 s_aw[DIRECT_BLOCK];   // per Gaussian: (slot of its first instance - index of its first tile, w | h << 16)
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);                    // [8][T]
+    uint32_t* s_base = s_mask + 8 * (size_t)T;                                    // [T]
+    unsigned char* s_wrank = reinterpret_cast<unsigned char*>(s_base + T);        // [8][T]
     __shared__ uint32_t s_w8[8];
 
     const int b = blockIdx.x;
@@ -667,13 +697,14 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so EMPTY ranges are
     // published -- the render then produces zeros without touching unwritten list entries -- and the host sees
     // status[1] = 1 (direct_scan) and re-runs with a larger buffer.
+    const uint32_t C = plan_chunk_for(status[0], pl.chunk_override);   // status[0] = R (direct_scan)
     const int npub = db.nb < DIRECT_BLOCK ? db.nb : DIRECT_BLOCK;
     const bool pub = (b < npub) && (tid % npub == b);
     const unsigned long long tot = cta_exclusive_scan_1pass<unsigned long long>(
         T,
         [&](int i) {
             const uint32_t c = tc[i];
-            return ((unsigned long long)(c ? (c - 1) / PLAN_CHUNK : 0u) << 32) | c;
+            return ((unsigned long long)(c ? (c - 1) / C : 0u) << 32) | c;
         },
         [&](int i, unsigned long long ex64, unsigned long long v64, unsigned long long total) {
             const uint32_t ex = (uint32_t)ex64, cnt = (uint32_t)v64;
@@ -693,7 +724,8 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     const uint32_t R = (uint32_t)tot;
     if (b == 0 && tid == 0) {
         pl.extra_off[T] = ((long long)R > capacity) ? 0u : (uint32_t)(tot >> 32);
-        pl.counter[0] = pl.counter[1] = pl.counter[2] = pl.counter[3] = 0;
+        pl.counter[0] = pl.counter[1] = pl.counter[3] = 0;
+        pl.counter[2] = C;
     }
     uint32_t wpre = 0;
 #pragma unroll
@@ -702,54 +734,57 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     const uint32_t lex = wpre + ia - n;
     if (g < P) offsets[g] = bbase + lex + n;     // inclusive scan, same meaning as the reference's point_offsets
     if ((long long)R > capacity) return;         // overflow: nothing may be written (uniform across the grid)
+    const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff, z1 = c45 >> 16;
     // mark
-    if (n) {
-        const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff,
-                       z1 = c45 >> 16;
-        // emission slot of instance (tx,ty,tz) = bbase + lex + ((tz-z0) h + (ty-y0)) w + (tx-x0)
-        //                                      = [bbase + lex - ((z0 h + y0) w + x0)] + (tz h + ty) w + tx   (mod 2^32)
-        const uint32_t w = x1 - x0, h = y1 - y0;
-        s_aw[tid] = make_uint2(bbase + lex - ((z0 * h + y0) * w + x0), w | (h << 16));
+    {
         uint32_t* plane = s_mask + (size_t)warp * T;
         const uint32_t bit = 1u << lane;
+        if (n)
+            for (uint32_t z = z0; z < z1; ++z)
+                for (uint32_t y = y0; y < y1; ++y) {
+                    const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
+                    for (uint32_t x = x0; x < x1; ++x) atomicOr(&plane[rowb + x], bit);
+                }
+    }
+    __syncthreads();
+    // rank of word w inside its tile's run = population of the words below it
+    for (int t = tid; t < T; t += DIRECT_BLOCK) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            s_wrank[(size_t)w * T + t] = (unsigned char)run;    // <= 224
+            run += __popc(s_mask[(size_t)w * T + t]);
+        }
+    }
+    __syncthreads();
+    // place: lane per instance, tiles of this thread's Gaussian in emission order (z, y, x ascending)
+    if (n) {
+        const uint32_t* plane = s_mask + (size_t)warp * T;
+        const unsigned char* wr = s_wrank + (size_t)warp * T;
+        const uint32_t below = (1u << lane) - 1u;
+        uint32_t slot = bbase + lex;
         for (uint32_t z = z0; z < z1; ++z)
             for (uint32_t y = y0; y < y1; ++y) {
                 const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
-                for (uint32_t x = x0; x < x1; ++x) atomicOr(&plane[rowb + x], bit);
+                for (uint32_t x = x0; x < x1; ++x) {
+                    const uint32_t t = rowb + x;
+                    const uint32_t pos = s_base[t] + wr[t] + __popc(plane[t] & below);
+                    point_list[pos] = (uint32_t)g;
+                    inst_pos[pos] = slot++;
+                }
             }
-    }
-    __syncthreads();
-    // place
-    const uint32_t gxy = (uint32_t)gx * (uint32_t)gy;
-    for (int t = tid; t < T; t += DIRECT_BLOCK) {
-        uint32_t pos = s_base[t];
-        const uint32_t tz = (uint32_t)t / gxy, rem = (uint32_t)t - tz * gxy, ty = rem / (uint32_t)gx,
-                       tx = rem - ty * (uint32_t)gx;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            uint32_t m = s_mask[(size_t)w * T + t];
-            while (m) {
-                const int bitpos = __ffs(m) - 1;
-                m &= m - 1;
-                const int gl = w * 32 + bitpos;
-                const uint2 aw = s_aw[gl];
-                point_list[pos] = (uint32_t)(b * DIRECT_BLOCK + gl);
-                inst_pos[pos] = aw.x + (tz * (aw.y >> 16) + ty) * (aw.y & 0xffffu) + tx;
-                ++pos;
-            }
-        }
     }
 }
 
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
                        const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
-                       int gy) {
-    const size_t smem = (size_t)db.num_tiles * 36;
+                       int gy, const uint32_t* status) {
+    const size_t smem = (size_t)db.num_tiles * 44;
     if (smem > 40 * 1024)
         R2X_CUDA_OK(cudaFuncSetAttribute(direct_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DIRECT_MAX_TILES * 36));
-    direct_fill_kernel<<<db.nb, DIRECT_BLOCK, smem, st>>>(P, cube, tiles_touched, offsets, db, ranges, plan,
-                                                              bv.point_list, bv.inst_pos, bv.capacity, gx, gy);
+                                         DIRECT_MAX_TILES * 44));
+    R2X_CUDA_OK(pdl_launch(direct_fill_kernel, dim3(db.nb), dim3(DIRECT_BLOCK), smem, st, P, cube, tiles_touched, offsets,
+                           db, ranges, plan, bv.point_list, bv.inst_pos, bv.capacity, gx, gy, status));
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }

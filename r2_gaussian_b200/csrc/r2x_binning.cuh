@@ -38,27 +38,47 @@ constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096
 constexpr int SORT_MAX_BLOCKS = 296;                   // 2 CTAs per SM on 148 SMs
 
 // ---- work plan for the per-tile kernels -------------------------------------------------------
-// Per-tile lists are cut into chunks of PLAN_CHUNK instances; a (tile, chunk) pair is one work item of
-// the render kernels, handed out through an atomic counter, so that SM load is balanced no matter how
-// uneven the per-tile counts are.  Items [0,T) are chunk 0 of every tile (also of empty tiles: they
-// write the zeros); items [T, T+E) are the extra chunks, looked up in `extra_item`.  A tile with several
-// chunks combines its partial sums in chunk order (the last-arriving CTA does it) => deterministic.
-constexpr int PLAN_CHUNK = 256;
+// Per-tile lists are cut into chunks of at most C instances (C = the launch's chunk size, 64..PLAN_CHUNK, chosen ON
+// THE DEVICE from the instance count R so that the item count stays a few times the number of resident CTAs:
+// plan_chunk_for); a tile of n instances gets ceil(n / C) chunks of EQUAL length (+-1).  A (tile, chunk) pair is one
+// work item of the render kernels, handed out through an atomic counter, so that SM load is balanced no matter how
+// uneven the per-tile counts are.  Items [0,T) are chunk 0 of every tile (also of empty tiles: they write the
+// zeros); items [T, T+E) are the extra chunks, looked up in `extra_item`.  A tile with several chunks combines its
+// partial sums in chunk order (the last-arriving CTA does it) => deterministic.
+constexpr int PLAN_CHUNK = 256;       // largest chunk = records staged per work item
+constexpr int PLAN_MIN_CHUNK = 64;    // smallest chunk (sizes extra_item / partial)
+constexpr int PLAN_TARGET_ITEMS = 148 * 6 * 4;   // aim: ~4 items per resident CTA of the raster render kernel
 constexpr int PLAN_DONE_SLOTS = 8;   // arrival counters per tile (one per warp of the raster render CTA)
 struct TilePlan {
     uint32_t* extra_off;  // [T+1] exclusive scan of (chunks_t - 1); [T] = E
     uint32_t* tile_done;  // [T][PLAN_DONE_SLOTS] arrival counters of multi-chunk tiles
-    uint32_t* counter;    // [4]   work-queue heads (0: forward, 1: backward)
-    uint2* extra_item;    // [R/PLAN_CHUNK + 1] (tile, chunk >= 1) of extra item j   (binning buffer)
-    float* partial;       // [R/PLAN_CHUNK + 1][512] partial sums of extra chunks      (binning buffer)
+    uint32_t* counter;    // [4]   0: forward queue head, 1: backward queue head, 2: chunk size C of this launch
+    uint2* extra_item;    // [R/PLAN_MIN_CHUNK + 1] (tile, chunk >= 1) of extra item j   (binning buffer)
+    float* partial;       // [R/PLAN_MIN_CHUNK + 1][512] partial sums of extra chunks      (binning buffer)
     int num_tiles;
+    int chunk_override;   // 0 = automatic (plan_chunk_for); else the chunk size to use (R2X_CHUNK, experiments)
     long long max_extra;  // entries in extra_item / partial
 };
+__host__ __device__ __forceinline__ uint32_t plan_chunk_for(uint32_t R, int chunk_override) {
+    if (chunk_override > 0) return (uint32_t)(chunk_override < PLAN_MIN_CHUNK ? PLAN_MIN_CHUNK : (chunk_override > PLAN_CHUNK ? PLAN_CHUNK : chunk_override));
+    uint32_t c = (R / PLAN_TARGET_ITEMS + 31u) & ~31u;
+    return c < (uint32_t)PLAN_MIN_CHUNK ? (uint32_t)PLAN_MIN_CHUNK : (c > (uint32_t)PLAN_CHUNK ? (uint32_t)PLAN_CHUNK : c);
+}
+int plan_chunk_override();   // R2X_CHUNK from the environment (0 when unset)
 size_t plan_bytes(int num_tiles);
 struct BinningView;
 TilePlan plan_view(void* image_buf_after_ranges, int num_tiles, const BinningView& bv);
 int launch_plan(cudaStream_t st, const uint2* ranges, const TilePlan& plan);
 int reset_plan_counter(cudaStream_t st, const TilePlan& plan, int which);
+
+// chunk `chunk` of `nch` equal slices of the tile list [r.x, r.y)
+__device__ __forceinline__ void plan_slice(const uint2 r, int chunk, int nch, uint32_t& begin, int& n) {
+    const uint32_t len = r.y - r.x;
+    const uint32_t lo = (uint32_t)(((unsigned long long)len * (uint32_t)chunk) / (uint32_t)nch);
+    const uint32_t hi = (uint32_t)(((unsigned long long)len * (uint32_t)(chunk + 1)) / (uint32_t)nch);
+    begin = r.x + lo;
+    n = (int)(hi - lo);
+}
 
 __device__ __forceinline__ void plan_decode(const TilePlan& pl, const uint2* __restrict__ ranges, uint32_t item,
                                             int& tile, int& chunk, int& nch, uint32_t& begin, int& n) {
@@ -66,9 +86,7 @@ __device__ __forceinline__ void plan_decode(const TilePlan& pl, const uint2* __r
     else { const uint2 e = pl.extra_item[item - pl.num_tiles]; tile = (int)e.x; chunk = (int)e.y; }
     nch = (int)(pl.extra_off[tile + 1] - pl.extra_off[tile]) + 1;
     const uint2 r = ranges[tile];
-    begin = r.x + (uint32_t)chunk * PLAN_CHUNK;
-    const int left = (int)(r.y - r.x) - chunk * PLAN_CHUNK;
-    n = left < PLAN_CHUNK ? (left > 0 ? left : 0) : PLAN_CHUNK;
+    plan_slice(r, chunk, nch, begin, n);
 }
 
 size_t binning_bytes(long long R);
@@ -130,7 +148,7 @@ int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, l
                        uint32_t* status_out);
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
                        const DirectBin& db, uint2* ranges, const TilePlan& plan, const BinningView& bv, int gx,
-                       int gy);
+                       int gy, const uint32_t* status);
 
 // Exclusive->inclusive scan of tiles_touched[P] into offsets[P]; total (R) is written to *d_total
 // (device) -- single pass, decoupled look-back.  scan_state needs scan_state_bytes(P) bytes, zeroed

@@ -40,14 +40,14 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerPack pk, int world, int rank, uint32_t epoch,
                                                              float* __restrict__ out, long long n,
-                                                             uint32_t* __restrict__ status) {
+                                                             uint32_t* __restrict__ status, long long timeout_cycles) {
     // 1. signal (one CTA), 2. wait (every CTA)
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(pk.flags[threadIdx.x] + rank, epoch);
     if (threadIdx.x < world) {
         const uint32_t* f = pk.flags[rank] + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-            if (clock64() - t0 > (1ll << 32)) {   // ~2 s: a peer never arrived; report instead of hanging the GPU
+            if (clock64() - t0 > timeout_cycles) {   // a peer never arrived; report instead of hanging the GPU
                 atomicExch(status, 1u);
                 break;
             }
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerPack pk, int wo
 }
 
 int launch_peer_allreduce(cudaStream_t st, int world, int rank, const float* const* bufs, uint32_t* const* flags,
-                          uint32_t epoch, float* out, long long n, uint32_t* status) {
+                          uint32_t epoch, float* out, long long n, uint32_t* status, long long timeout_cycles) {
     if (world < 1 || world > R2X_MAX_PEERS || rank < 0 || rank >= world)
         return fail_msg(R2X_ERR_INVALID, "r2x_peer_allreduce_sum: bad world/rank");
     if (!bufs || !flags || !out || !status || n < 0) return fail_msg(R2X_ERR_INVALID, "r2x_peer_allreduce_sum: null pointer");
@@ -92,7 +92,8 @@ int launch_peer_allreduce(cudaStream_t st, int world, int rank, const float* con
     long long nb = ((n >> 2) + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > 148) nb = 148;     // all CTAs spin on the flags: keep the grid within one wave
-    peer_allreduce_kernel<<<(unsigned)nb, 256, 0, st>>>(pk, world, rank, epoch, out, n, status);
+    if (timeout_cycles <= 0) timeout_cycles = 1ll << 32;   // ~2 s
+    peer_allreduce_kernel<<<(unsigned)nb, 256, 0, st>>>(pk, world, rank, epoch, out, n, status, timeout_cycles);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -138,7 +139,13 @@ int r2x_ipc_close(void* dev_ptr) {
 
 int r2x_peer_allreduce_sum(void* stream, int world, int rank, const float* const* bufs, uint32_t* const* flags,
                            uint32_t epoch, float* out, long long n, uint32_t* status_dev) {
-    return r2x::launch_peer_allreduce((cudaStream_t)stream, world, rank, bufs, flags, epoch, out, n, status_dev);
+    return r2x::launch_peer_allreduce((cudaStream_t)stream, world, rank, bufs, flags, epoch, out, n, status_dev, 0);
+}
+
+int r2x_peer_allreduce_sum_t(void* stream, int world, int rank, const float* const* bufs, uint32_t* const* flags,
+                             uint32_t epoch, float* out, long long n, uint32_t* status_dev, long long timeout_cycles) {
+    return r2x::launch_peer_allreduce((cudaStream_t)stream, world, rank, bufs, flags, epoch, out, n, status_dev,
+                                      timeout_cycles);
 }
 
 }  // extern "C"

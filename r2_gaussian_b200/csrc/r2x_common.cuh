@@ -117,6 +117,31 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched through pdl_launch() may become resident while its
+// predecessor in the stream is still running; it parks in pdl_wait() until that predecessor has completed and its
+// writes are visible, so the launch latency and the CTA ramp of every kernel of a forward / backward chain overlap
+// the tail of the previous one.  Every kernel launched this way calls pdl_prologue() before touching global memory
+// (inputs may be outputs of the predecessor, outputs may still be read by it) and thereby lets its own successor in.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // atomicAdd with release semantics at gpu scope: everything this thread (and, through a preceding warp/CTA
 // barrier, its peers) wrote before is visible to whoever observes the incremented value.  Cheaper than
 // __threadfence() + atomicAdd, and it does not invalidate the SM's L1.
@@ -124,6 +149,26 @@ __device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* addr, uint32_
     uint32_t old;
     asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
     return old;
+}
+
+// packed FP32 pairs (sm_100: FMUL2 / FFMA2 -- one issue slot for two lanes of math)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -7,9 +7,10 @@ namespace r2x {
 
 // Per-Gaussian projected state ("geometry buffer"), device pointers carved from the caller's buffer.
 struct RasterGeom {
-    float4* rec;              // [2P] (pix_x, pix_y, log2(w = rho*mu), 0 [fast path] | w [exact path]), (A,B,C scaled by log2e/2, log2e, log2e/2, mu)
+    float4* rec;              // [2P] (pix_x, pix_y, log2(w = rho*mu), 0 [fast path] | w [exact path]), (A,B,C scaled by log2e/2, log2e, log2e/2, K = 2^(-2 A2))
     float4* aux;              // [P]  (A, B, C, rho) raw conic + density (backward / parity export)
     float* depth;             // [P]  view-space depth (the low half of the reference's sort key)
+    float* mu;                // [P]  integration factor mu (backward / parity export)
     uint16_t* cube;           // [6P] tile rectangle x0,y0,0,x1,y1,1
     uint32_t* tiles_touched;  // [P]
     uint32_t* offsets;        // [P] inclusive scan of tiles_touched

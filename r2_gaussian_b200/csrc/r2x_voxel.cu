@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
     int rxi = 0, ryi = 0, rzi = 0;
     uint32_t ntiles = 0, c01 = 0, c23 = 0, c45 = 0;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    float depth_out = 0.f;
 
     float c3[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (!live) {
@@ -150,10 +151,12 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
                                    inv[2] * (inv[1] * inv[4] - inv[3] * inv[2]);
                 const bool pd = (inv[0] > 0.0f) && (inv[3] > 0.0f) && (inv[5] > 0.0f) && (m01 > 1e-4f * inv[0] * inv[3]) &&
                                 (det3 > 1e-4f * inv[0] * inv[3] * inv[5]);
-                const bool fast = !(rho > 0.0f) || (pd && F2 <= 2.0f);
+                const bool fast = !(rho > 0.0f) || (pd && F2 <= 2.0f && lw <= 20.0f && lw >= -100.0f);
                 r0 = make_float4(pvx, pvy, pvz, lw);
                 r1 = make_float4(inv[0] * (0.5f * LOG2E), inv[1] * LOG2E, inv[2] * LOG2E, inv[3] * (0.5f * LOG2E));
-                r2 = make_float4(inv[4] * LOG2E, F2, mz, fast ? 0.0f : rho);
+                // r2.z = K = 2^(-2 F2): ratio of the multiplicative forward differences along z (voxel_fast_8)
+                r2 = make_float4(inv[4] * LOG2E, F2, (float)exp2(-2.0 * (double)F2), fast ? 0.0f : rho);
+                depth_out = mz;
                 c01 = (uint32_t)x0 | ((uint32_t)y0 << 16);
                 c23 = (uint32_t)z0 | ((uint32_t)x1 << 16);
                 c45 = (uint32_t)y1 | ((uint32_t)z1 << 16);
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
         geom.rec[4 * (size_t)g + 0] = r0;
         geom.rec[4 * (size_t)g + 1] = r1;
         geom.rec[4 * (size_t)g + 2] = r2;
-        geom.rec[4 * (size_t)g + 3] = make_float4(rho, 0.f, 0.f, 0.f);   // backward / export only (never gathered)
+        geom.rec[4 * (size_t)g + 3] = make_float4(rho, depth_out, 0.f, 0.f);   // backward / export only (never gathered)
         uint32_t* cu = reinterpret_cast<uint32_t*>(geom.cube + 6 * (size_t)g);
         cu[0] = c01; cu[1] = c23; cu[2] = c45;
     }
@@ -197,17 +200,21 @@ __device__ __forceinline__ VWorkItem vfetch_item(const TilePlan& pl, const uint2
 
 constexpr float VQ_CUT = 19.931568569324174f;   // log2(1e6): alpha = 2^-q >= 1e-6  <=>  q <= VQ_CUT
 
-__device__ __forceinline__ void vadd_if_le(float& acc, float e, float q) {
+// acc += e  iff  e >= 1e-6   (FSETP + predicated FADD; a NaN never passes)
+__device__ __forceinline__ void vadd_if_alpha(float& acc, float e) {
     asm("{\n"
         ".reg .pred p;\n"
-        "setp.le.f32 p, %2, %3;\n"
+        "setp.ge.f32 p, %1, 0f358637BD;\n"
         "@p add.f32 %0, %0, %1;\n"
         "}\n"
         : "+f"(acc)
-        : "f"(e), "f"(q), "f"(VQ_CUT));
+        : "f"(e));
 }
 
-// 8 voxels of one z column.  q(k) = q0 + lin*dz + F2*dz^2 with dz = dz0 - k, minus log2 rho.
+// 8 voxels of one z column.  q(k) = q0 + lin*dz + F2*dz^2 - log2 rho with dz = dz0 - k has constant second
+// differences along z, so alpha(k) = 2^-q(k) advances by multiplicative forward differences exactly as in
+// r2x_raster.cu::render_fast_8: alpha(k+1) = alpha(k) D(k), D(k+1) = D(k) K, K = 2^(-2 F2) = r2.z; runs of 4 voxels,
+// the column's two runs packed in f32x2 registers; the reference's alpha < 1e-6 skip is tested on alpha itself.
 __device__ __forceinline__ void voxel_fast_8(float (&acc)[8], const float4 r0, const float4 r1, const float4 r2,
                                              float fx, float fy, float fz0) {
     const float dx = r0.x - fx, dy = r0.y - fy, dz0 = r0.z - fz0;
@@ -215,18 +222,24 @@ __device__ __forceinline__ void voxel_fast_8(float (&acc)[8], const float4 r0, c
     const float lin = fmaf(r1.z, dx, r2.x * dy);
     const float a2 = r2.y + r2.y;
     const float e0 = r2.y - lin;                      // d(k) = e0 - a2 (dz0 - k)
+    const uint64_t DZ = pack2(dz0, dz0 - 4.0f);
+    const uint64_t Q = fma2(DZ, fma2(pack2(r2.y, r2.y), DZ, pack2(lin, lin)), pack2(q0, q0));
+    const uint64_t Dd = fma2(pack2(-a2, -a2), DZ, pack2(e0, e0));
+    float qa, qb, da, db, ea, eb;
+    unpack2(Q, qa, qb);
+    unpack2(Dd, da, db);
+    uint64_t E = pack2(ex2_approx(-qa), ex2_approx(-qb)), D = pack2(ex2_approx(-da), ex2_approx(-db));
+    const uint64_t K = pack2(r2.z, r2.z);
+    unpack2(E, ea, eb);
+    vadd_if_alpha(acc[0], ea);
+    vadd_if_alpha(acc[4], eb);
 #pragma unroll
-    for (int h4 = 0; h4 < 2; ++h4) {
-        const float dza = dz0 - (float)(4 * h4);
-        float q = fmaf(dza, fmaf(r2.y, dza, lin), q0);
-        float d = fmaf(-a2, dza, e0);
-        vadd_if_le(acc[4 * h4], ex2_approx(-q), q);
-#pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            q += d;
-            d += a2;
-            vadd_if_le(acc[4 * h4 + k], ex2_approx(-q), q);
-        }
+    for (int k = 1; k < 4; ++k) {
+        E = mul2(E, D);
+        if (k < 3) D = mul2(D, K);
+        unpack2(E, ea, eb);
+        vadd_if_alpha(acc[k], ea);
+        vadd_if_alpha(acc[4 + k], eb);
     }
 }
 
@@ -412,6 +425,9 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
         const float qmax = VQ_CUT + r0.w;   // contributes iff 0 <= q <= log2(rho / 1e-6)
         const uint32_t lim = (qmax >= 0.0f) ? (__float_as_uint(qmax) + 1u) : 0u;
         const float dz0 = r0.z - fz0;
+        const bool fast = (r2.w == 0.0f);
+        const float a2 = r2.y + r2.y;
+        const float gcut = ex2_approx(-qmax);     // alpha = rho G >= 1e-6  <=>  G >= 2^-(VQ_CUT + log2 rho)
 #pragma unroll 1
         for (int ix = 0; ix < R2X_VTILE; ++ix) {
             const float dx = r0.x - (fx0 + (float)ix);
@@ -425,17 +441,40 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
                 const float4 db = *reinterpret_cast<const float4*>(&s_dl[ix][iy][4]);
                 const float dlv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
                 float R0 = 0.f, Rz = 0.f, Rzz = 0.f;
+                if (fast) {
+                    // G(k) = 2^-quad(k) by multiplicative forward differences along z (voxel_fast_8); moments are taken
+                    // about the voxel index k (immediates) and shifted to dz = dz0 - k afterwards
+                    float N0 = 0.f, N1 = 0.f, N2 = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float dz = dz0 - (float)k;
-                    const float u = fmaf(r2.y, dz, lin);
-                    const float qq = fmaf(dz, u, q0);
-                    const float G = ex2_approx(-qq);
-                    const float t = (__float_as_uint(qq) < lim) ? dlv[k] * G : 0.f;
-                    R0 += t;
-                    const float tdz = t * dz;
-                    Rz += tdz;
-                    Rzz = fmaf(tdz, dz, Rzz);
+                    for (int h4 = 0; h4 < 2; ++h4) {
+                        const float dza = dz0 - (float)(4 * h4);
+                        float G = ex2_approx(-fmaf(dza, fmaf(r2.y, dza, lin), q0));
+                        float D = ex2_approx(-fmaf(-a2, dza, r2.y - lin));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k > 0) { G *= D; if (k < 3) D *= r2.z; }
+                            const float t = (G >= gcut) ? dlv[4 * h4 + k] * G : 0.f;
+                            N0 += t;
+                            N1 = fmaf(t, (float)(4 * h4 + k), N1);
+                            N2 = fmaf(t, (float)((4 * h4 + k) * (4 * h4 + k)), N2);
+                        }
+                    }
+                    R0 = N0;
+                    Rz = fmaf(dz0, N0, -N1);
+                    Rzz = fmaf(dz0, fmaf(dz0, N0, -2.0f * N1), N2);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dz = dz0 - (float)k;
+                        const float u = fmaf(r2.y, dz, lin);
+                        const float qq = fmaf(dz, u, q0);
+                        const float G = ex2_approx(-qq);
+                        const float t = (__float_as_uint(qq) < lim) ? dlv[k] * G : 0.f;
+                        R0 += t;
+                        const float tdz = t * dz;
+                        Rz += tdz;
+                        Rzz = fmaf(tdz, dz, Rzz);
+                    }
                 }
                 X0 += R0; Xz += Rz; Xzz += Rzz;
                 Xy = fmaf(dy, R0, Xy);

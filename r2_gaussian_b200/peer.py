@@ -24,7 +24,7 @@ class _DevArray:
 
 
 class PeerReducer:
-    def __init__(self, numel: int, device, group=None):
+    def __init__(self, numel: int, device, group=None, timeout_s: float = 20.0):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerReducer needs an initialised torch.distributed process group")
         self.lib = load()
@@ -34,6 +34,7 @@ class PeerReducer:
         if self.world > MAX_PEERS:
             raise RuntimeError(f"PeerReducer supports at most {MAX_PEERS} ranks")
         self.numel = int(numel)
+        self.timeout_cycles = int(max(timeout_s, 0.001) * 1.9e9)   # SM clock cycles the kernel waits for a peer
         self.stride = (self.numel * 4 + 255) // 256 * 256
         nbytes = 2 * self.stride + 256
         with torch.cuda.device(self.device):
@@ -72,9 +73,9 @@ class PeerReducer:
         if out.numel() != self.numel or out.dtype != torch.float32 or not out.is_contiguous():
             raise RuntimeError("PeerReducer.reduce: out must be a contiguous float32 tensor of the reducer's size")
         self.epoch += 1
-        rc = self.lib.r2x_peer_allreduce_sum(torch.cuda.current_stream(self.device).cuda_stream, self.world, self.rank,
-                                             self._bufs[self.epoch & 1], self._flags, self.epoch & 0xFFFFFFFF,
-                                             out.data_ptr(), self.numel, self.status.data_ptr())
+        rc = self.lib.r2x_peer_allreduce_sum_t(torch.cuda.current_stream(self.device).cuda_stream, self.world, self.rank,
+                                               self._bufs[self.epoch & 1], self._flags, self.epoch & 0xFFFFFFFF,
+                                               out.data_ptr(), self.numel, self.status.data_ptr(), self.timeout_cycles)
         check(rc, "r2x_peer_allreduce_sum")
         return out
 

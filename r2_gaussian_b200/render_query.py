@@ -4,8 +4,9 @@ Same contract as r2_gaussian/gaussian/render_query.py of the reference (query :2
 `pc` is any object exposing get_xyz / get_density / get_scaling / get_rotation (and get_covariance when
 pipe.compute_cov3D_python), `viewpoint_camera` exposes image_height/width, FoVx/FoVy, mode,
 world_view_transform, full_proj_transform, camera_center; `pipe` exposes debug and compute_cov3D_python.
-Under torch.distributed (world > 1) each rank holds a shard of the Gaussians and the image / volume is
-summed over ranks (sharded.py); the per-Gaussian outputs describe the local shard.
+After `sharded.enable(group)` (Gaussian-sharded runs: the trainer, bench.py) each rank holds a shard of the
+Gaussians and the image / volume is summed over ranks; the per-Gaussian outputs describe the local shard.
+Without that opt-in an initialised process group changes nothing (data-parallel / multi-scene jobs).
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ import math
 import torch
 
 from .rasterization import GaussianRasterizationSettings, GaussianRasterizer
-from .sharded import all_reduce_sum
+from .sharded import sharded_sum
 from .voxelization import GaussianVoxelizationSettings, GaussianVoxelizer
 
 
@@ -35,7 +36,7 @@ def query(pc, center, nVoxel, sVoxel, pipe, scaling_modifier=1.0):
     scales, rotations, cov3D = _covariance_inputs(pc, pipe, scaling_modifier)
     vol, radii = GaussianVoxelizer(voxel_settings=settings)(
         means3D=pc.get_xyz, opacities=pc.get_density, scales=scales, rotations=rotations, cov3D_precomp=cov3D)
-    return {"vol": all_reduce_sum(vol), "radii": radii}
+    return {"vol": sharded_sum(vol), "radii": radii}
 
 
 def render(viewpoint_camera, pc, pipe, scaling_modifier=1.0):
@@ -66,5 +67,5 @@ def render(viewpoint_camera, pc, pipe, scaling_modifier=1.0):
     image, radii = GaussianRasterizer(raster_settings=settings)(
         means3D=xyz, means2D=screenspace_points, opacities=pc.get_density, scales=scales, rotations=rotations,
         cov3D_precomp=cov3D)
-    return {"render": all_reduce_sum(image), "viewspace_points": screenspace_points,
+    return {"render": sharded_sum(image), "viewspace_points": screenspace_points,
             "visibility_filter": radii > 0, "radii": radii}

@@ -31,6 +31,33 @@ def world_info() -> tuple[int, int]:
 
 
 _PEER = {"on": False, "reducers": {}}
+_SHARD = {"on": False, "group": None}
+
+
+def enable(group=None, on: bool = True):
+    """Declare that THIS process group runs Gaussian-sharded: every rank holds a slice of one cloud and render() /
+    query() must sum their images / volumes over the ranks.  Sharding is an explicit opt-in (the trainer and bench.py
+    call this): a data-parallel or multi-scene job that merely has torch.distributed initialised keeps per-rank images."""
+    _SHARD["on"], _SHARD["group"] = bool(on), (group if on else None)
+
+
+def enabled() -> bool:
+    return bool(_SHARD["on"]) and dist.is_available() and dist.is_initialized()
+
+
+def sharded_sum(x: torch.Tensor) -> torch.Tensor:
+    """all_reduce_sum over the sharding group when sharding is enabled, identity otherwise (render() / query())."""
+    return all_reduce_sum(x, _SHARD["group"]) if enabled() else x
+
+
+def check_peer_exchange():
+    """Raise if any peer-memory reduction since the last check gave up waiting for a peer (the kernel sets a status word
+    instead of hanging the GPU, and then sums whatever the late peer's buffer held).  Synchronises; the trainer calls it
+    where it synchronises anyway (loss read-outs, saves, evaluations)."""
+    bad = [k for k, r in _PEER["reducers"].items() if not r.ok()]
+    if bad:
+        raise RuntimeError(f"r2x_peer_allreduce_sum: a peer did not arrive within the time-out for buffers {bad}; the "
+                           "summed images since the last check are invalid (rank skew, e.g. rank-0-only I/O without a barrier)")
 
 
 def enable_peer_exchange(on: bool = True):

@@ -31,6 +31,7 @@ from .dataset import Scene
 from .gaussian_model import GaussianModel
 from .metrics import metric_proj, metric_vol
 from .render_query import query, render
+from . import sharded
 from .sharded import gather_point_cloud, shard_init_points, world_info
 
 
@@ -144,6 +145,7 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     rank, world = world_info()
     dist2 = None
     if world > 1:
+        sharded.enable()
         # Gaussian-sharded run (one process per GPU, torchrun): every rank owns an index slice of the cloud, its
         # Adam state and its densification; render() / query() sum the partial images / volumes over the ranks, so
         # loss and gradients are what a single GPU would compute.  3-NN distances come from the FULL cloud.
@@ -156,9 +158,15 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     scene.gaussians = gaussians
     gaussians.training_setup(opt)
     if checkpoint is not None:
-        model_state, first_iter = torch.load(checkpoint, weights_only=False)
+        path = rank_checkpoint_path(checkpoint, rank, world)
+        payload = torch.load(path, weights_only=False)
+        model_state, first_iter = payload[0], payload[1]
+        tag = payload[2] if len(payload) > 2 else {"rank": 0, "world": 1}
+        if (tag["rank"], tag["world"]) != (rank, world):
+            raise RuntimeError(f"checkpoint {path} was written by rank {tag['rank']} of {tag['world']}; this process is "
+                               f"rank {rank} of {world} (a Gaussian-sharded run resumes with the same number of ranks)")
         gaussians.restore(model_state, opt)
-        log(f"Load checkpoint {os.path.basename(checkpoint)}.")
+        log(f"Load checkpoint {os.path.basename(path)}.")
 
     use_tv = opt.lambda_tv > 0
     tv_n = ds["tv_vol_nVoxel"]
@@ -193,7 +201,11 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                     and iteration % opt.densification_interval == 0:
                 gaussians.densify_and_prune(opt.densify_grad_threshold, opt.density_min_threshold, opt.max_screen_size,
                                             ds["max_scale"], opt.max_num_gaussians, ds["densify_scale_threshold"], bbox)
-            if gaussians.get_density.shape[0] == 0:
+            # sharded: an EMPTY SHARD is fine and keeps going through the P == 0 path; the run stops -- on every rank at
+            # once, so nobody is left waiting in a collective -- only when the whole cloud is gone (the count can only
+            # change at a densification step, which is where the all-reduce is paid)
+            if (world == 1 and gaussians.get_density.shape[0] == 0) or \
+                    (world > 1 and iteration % opt.densification_interval == 0 and total_gaussians(gaussians, world) == 0):
                 raise ValueError("No Gaussian left. Change adaptive control hyperparameters!")
             if iteration < opt.iterations:
                 gaussians.optimizer.step()
@@ -206,19 +218,75 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                     save_sharded(scene, gaussians, iteration, queryfunc, rank)
             if scene.model_path and iteration in checkpoint_iterations:
                 log(f"[ITER {iteration}] Saving Checkpoint")
-                name = f"chkpnt{iteration}.pth" if world == 1 else f"chkpnt{iteration}_rank{rank}.pth"
-                torch.save((gaussians.capture(), iteration), os.path.join(ckpt_dir, name))
+                name = os.path.basename(rank_checkpoint_path(f"chkpnt{iteration}.pth", rank, world))
+                payload = (gaussians.capture(), iteration) if world == 1 else \
+                    (gaussians.capture(), iteration, {"rank": rank, "world": world})
+                torch.save(payload, os.path.join(ckpt_dir, name))
+                if world > 1:
+                    torch.distributed.barrier()      # no rank runs ahead into the next exchange while others write
             if iteration % 100 == 0:
                 history["loss"].append((iteration, float(total)))
+                if world > 1:
+                    sharded.check_peer_exchange()    # the loss read-out above synchronised anyway
             if iteration in testing_iterations:
                 history["eval"][iteration] = evaluate(scene, gaussians, pipe)
                 log(f"[ITER {iteration}] {history['eval'][iteration]}  points {gaussians.get_xyz.shape[0]}")
+                if world > 1:
+                    sharded.check_peer_exchange()
+                if scene.model_path and rank == 0:
+                    write_eval_yaml(scene.model_path, iteration, history["eval"][iteration])
     torch.cuda.synchronize()
     history["seconds"] = time.perf_counter() - t_start
     history["iterations"] = opt.iterations - first_iter
     history["gaussians"] = int(gaussians.get_xyz.shape[0])
     history["scene"], history["model"] = scene, gaussians
     return history
+
+
+def rank_checkpoint_path(path: str, rank: int, world: int) -> str:
+    """`chkpntN.pth` for a single-GPU run, `chkpntN_rank{r}.pth` for rank r of a Gaussian-sharded run (any existing
+    `_rank{k}` suffix of the given path is replaced, so the same --start_checkpoint works on every rank)."""
+    import re
+    if world == 1:
+        return path
+    stem, ext = os.path.splitext(path)
+    stem = re.sub(r"_rank\d+$", "", stem)
+    return f"{stem}_rank{rank}{ext}"
+
+
+def total_gaussians(gaussians: GaussianModel, world: int) -> int:
+    n = int(gaussians.get_xyz.shape[0])
+    if world == 1:
+        return n
+    t = torch.tensor([n], device="cuda", dtype=torch.int64)
+    torch.distributed.all_reduce(t)
+    return int(t.item())
+
+
+def write_eval_yaml(model_path: str, iteration: int, ev: dict):
+    """`eval/iter_xxxxxx/eval3d.yml` + `eval2d_render_{train,test}.yml` with the reference's keys (`train.py:283-330`)."""
+    import yaml
+    out = os.path.join(model_path, "eval", f"iter_{iteration:06d}")
+    os.makedirs(out, exist_ok=True)
+    d3 = {k: float(v) for k, v in ev.items() if k.endswith("_3d")}
+    with open(os.path.join(out, "eval3d.yml"), "w") as f:
+        yaml.dump(d3, f, default_flow_style=False, sort_keys=False)
+    for name in ("train", "test"):
+        d2 = {k.replace(f"_{name}", ""): float(v) for k, v in ev.items() if k.endswith(f"_2d_{name}")}
+        if d2:
+            with open(os.path.join(out, f"eval2d_render_{name}.yml"), "w") as f:
+                yaml.dump(d2, f, default_flow_style=False, sort_keys=False)
+
+
+def write_cfg_args(model_path: str, model, pipe, opt, extra: dict):
+    """`<model_path>/cfg_args`: the Namespace repr the reference's test.py evaluates (`arguments/__init__.py:74-95`,
+    written by `utils/log_utils.py:28-29`), with the reference's field names, next to a JSON copy."""
+    from argparse import Namespace
+    flat = {**asdict(model), **asdict(pipe), **asdict(opt), **extra}
+    with open(os.path.join(model_path, "cfg_args"), "w") as f:
+        f.write(str(Namespace(**flat)))
+    with open(os.path.join(model_path, "cfg_args.json"), "w") as f:
+        json.dump({"model": asdict(model), "pipe": asdict(pipe), "opt": asdict(opt)}, f, indent=1)
 
 
 def save_sharded(scene: Scene, gaussians: GaussianModel, iteration: int, queryfunc, rank: int):
@@ -228,14 +296,17 @@ def save_sharded(scene: Scene, gaussians: GaussianModel, iteration: int, queryfu
     out = os.path.join(scene.model_path, "point_cloud/iteration_{}".format(iteration))
     merged = gather_point_cloud(gaussians)
     vol_pred = queryfunc(gaussians)["vol"] if queryfunc is not None else None
-    if rank != 0:
-        return
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "point_cloud.pickle"), "wb") as f:
-        pickle.dump(merged, f, pickle.HIGHEST_PROTOCOL)
-    if vol_pred is not None:
-        np.save(os.path.join(out, "vol_gt.npy"), scene.vol_gt.detach().cpu().numpy())
-        np.save(os.path.join(out, "vol_pred.npy"), vol_pred.detach().cpu().numpy())
+    if rank == 0:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "point_cloud.pickle"), "wb") as f:
+            pickle.dump(merged, f, pickle.HIGHEST_PROTOCOL)
+        if vol_pred is not None:
+            np.save(os.path.join(out, "vol_gt.npy"), scene.vol_gt.detach().cpu().numpy())
+            np.save(os.path.join(out, "vol_pred.npy"), vol_pred.detach().cpu().numpy())
+    # rank 0 alone does the file I/O: nobody may run ahead into the next exchange (the peer-memory kernel waits a
+    # bounded time for late ranks), and any reduction that gave up since the last check is reported here
+    torch.distributed.barrier()
+    sharded.check_peer_exchange()
 
 
 def _add_dataclass_args(parser, cls, skip=()):
@@ -272,8 +343,10 @@ def main(argv=None):
         model.model_path = os.path.join("./output", os.path.basename(model.source_path.rstrip("/")))
     os.makedirs(model.model_path, exist_ok=True)
     if int(os.environ.get("RANK", "0")) == 0:
-        with open(os.path.join(model.model_path, "cfg_args.json"), "w") as f:
-            json.dump({"model": asdict(model), "pipe": asdict(pipe), "opt": asdict(opt)}, f, indent=1)
+        write_cfg_args(model.model_path, model, pipe, opt,
+                       {"test_iterations": a.test_iterations, "save_iterations": a.save_iterations,
+                        "checkpoint_iterations": a.checkpoint_iterations, "start_checkpoint": a.start_checkpoint,
+                        "quiet": False, "config": None, "detect_anomaly": False})
     random.seed(a.seed), np.random.seed(a.seed), torch.manual_seed(a.seed)     # safe_state (`general_utils.py:61-63`)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:                      # launched by torchrun: one process per GPU, Gaussians sharded by index
@@ -282,6 +355,7 @@ def main(argv=None):
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sharded.enable()                       # Gaussian sharding is an explicit opt-in of render() / query()
         if a.peer_exchange:
             from .sharded import enable_peer_exchange
             enable_peer_exchange(True)
@@ -292,6 +366,7 @@ def main(argv=None):
         import torch.distributed as dist
         from .sharded import enable_peer_exchange
         enable_peer_exchange(False)
+        sharded.enable(on=False)
         rank0 = dist.get_rank() == 0
         dist.barrier()
         dist.destroy_process_group()

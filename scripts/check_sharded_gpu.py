@@ -8,11 +8,13 @@ from types import SimpleNamespace
 import util
 from r2_gaussian_b200 import scene
 from r2_gaussian_b200.render_query import render, query
+from r2_gaussian_b200 import sharded
 from r2_gaussian_b200.sharded import shard_bounds, enable_peer_exchange
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+sharded.enable()                   # Gaussian sharding is an explicit opt-in of render() / query()
 if "--p2p" in sys.argv:
     enable_peer_exchange(True)     # NVLink peer-memory sum instead of NCCL for the image / volume exchange
 cloud, view = util.case("cone_trained_mid")

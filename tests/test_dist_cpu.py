@@ -81,3 +81,45 @@ def test_merge_point_clouds_orders_by_rank():
     assert m["xyz"].shape == (4, 3) and m["xyz"][:2].max() == 0 and m["xyz"][2:].min() == 1 and m["scale_bound"] is None
     with pytest.raises(ValueError):
         merge_point_clouds([])
+
+
+def _worker_opt_in(rank, world, port, q):
+    """render()/query() sum over ranks only after sharded.enable(); an initialised group alone changes nothing."""
+    import torch.distributed as dist
+    from r2_gaussian_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.full((4,), float(rank + 1))
+        a = sharded.sharded_sum(x).clone()
+        sharded.enable()
+        b = sharded.sharded_sum(x).clone()
+        sharded.enable(on=False)
+        c = sharded.sharded_sum(x).clone()
+        q.put((rank, a.tolist(), b.tolist(), c.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_is_an_explicit_opt_in():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_opt_in, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, a, b, c in res:
+        assert a == [rank + 1.0] * 4 and c == [rank + 1.0] * 4     # untouched without the opt-in
+        assert b == [3.0] * 4                                      # 1 + 2 once sharding is enabled
+
+
+def test_rank_checkpoint_paths():
+    from r2_gaussian_b200.trainer import rank_checkpoint_path
+    assert rank_checkpoint_path("ckpt/chkpnt100.pth", 0, 1) == "ckpt/chkpnt100.pth"
+    assert rank_checkpoint_path("ckpt/chkpnt100.pth", 3, 8) == "ckpt/chkpnt100_rank3.pth"
+    assert rank_checkpoint_path("ckpt/chkpnt100_rank0.pth", 5, 8) == "ckpt/chkpnt100_rank5.pth"
