@@ -189,6 +189,25 @@ typedef struct r2x_adam_group {
 int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
                   long long step);
 
+/* ---- device-side row compaction for densify / clone / split / prune ------------------------------ */
+/* Replaces the boolean-mask indexing + torch.cat sequence of the reference's optimizer surgery
+ * (r2_gaussian/gaussian/gaussian_model.py:335-403, :503-550).  r2x_mask_select turns a byte mask into the stable
+ * list of selected row indices and their count, both on the device (no host round trip).  r2x_gather_rows gathers up
+ * to R2X_GATHER_MAX_TENSORS row-major float tensors through one such list in ONE launch: source row s of tensor t is
+ * src0[s] for s < n0, else src1[s - n0] (src1 == NULL: zeros -- fresh Adam moments); `select` == NULL: identity. */
+#define R2X_GATHER_MAX_TENSORS 16
+typedef struct r2x_gather_desc {
+    const float* src0;   /* [n0, width]                          */
+    const float* src1;   /* [*, width] rows appended after src0, or NULL = zeros */
+    float* dst;          /* [nsel, width]                        */
+    long long n0;
+    int width;
+} r2x_gather_desc;
+size_t r2x_mask_select_scratch_bytes(int n);
+int r2x_mask_select(void* stream, int n, const unsigned char* mask, int* idx_out, uint32_t* count_dev, void* scratch,
+                    size_t scratch_bytes);
+int r2x_gather_rows(void* stream, int ntensors, const r2x_gather_desc* descs, const int* select, long long nsel);
+
 /* ---- multi-GPU exchange step: one-shot sum over NVLink peer memory ------------------------------ */
 /* The Gaussian-sharded projector (one process per GPU, every rank renders its index shard) needs ONE exchange per
  * projection: the sum of the per-rank partial detector images (BASELINE north_star; the reference itself is

@@ -10,6 +10,8 @@ stream only.  There is no CPU path: non-CUDA inputs raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
 
 import torch
 
@@ -60,6 +62,16 @@ class _Workspace:
     Capacities are rounded to a coarse grid so that torch's caching allocator sees repeating sizes."""
 
     hints: dict = {}
+    _pinned: list = []
+
+    @classmethod
+    def pinned_status(cls):
+        return cls._pinned.pop() if cls._pinned else torch.zeros(2, dtype=torch.int32).pin_memory()
+
+    @classmethod
+    def release(cls, t):
+        if len(cls._pinned) < 16:
+            cls._pinned.append(t)
 
     @staticmethod
     def _round(n: int) -> int:
@@ -78,22 +90,84 @@ class _Workspace:
         cls.hints[key] = want if want > cur or want < cur // 2 else cur
 
 
+class CapacityOverflow(RuntimeError):
+    """A speculative forward (see `speculative`) needed more (Gaussian, tile) instances than its binning buffer was
+    provisioned for; its image / volume is all zeros.  Raised by the matching backward (or by `NumRendered.resolve()`);
+    the capacity hint has been raised, so simply repeating the iteration succeeds."""
+
+
 class NumRendered(int):
     """`num_rendered` as the reference returns it (a Python int) that also remembers the instance capacity the
     binning buffer was carved for: the backward must carve the buffer with the same number.  The autograd
-    bridges keep this object in `ctx` and hand it back unchanged, exactly like the reference's plain int."""
+    bridges keep this object in `ctx` and hand it back unchanged, exactly like the reference's plain int.
+
+    After a speculative forward the integer value is the provisioned capacity (an upper bound) and `pending` holds
+    the pinned status word + event; `resolve()` waits for that event (long past by the time the backward runs),
+    returns the exact count and raises CapacityOverflow if the forward had overflowed."""
 
     capacity: int
+    pending = None
 
-    def __new__(cls, value: int, capacity: int | None = None):
+    def __new__(cls, value: int, capacity: int | None = None, pending=None):
         obj = super().__new__(cls, int(value))
         obj.capacity = int(value if capacity is None else capacity)
+        obj.pending = pending
         return obj
+
+    def resolve(self) -> int:
+        if self.pending is None:
+            return int(self)
+        host, event, key = self.pending
+        event.synchronize()
+        R, overflow = int(host[0]), int(host[1])
+        self.pending = None
+        _Workspace.update(key, R)
+        _Workspace.release(host)
+        if overflow:
+            raise CapacityOverflow(f"forward needed {R} instances, binning buffer provisioned for {self.capacity}; "
+                                   "the capacity hint has been raised -- repeat the iteration")
+        return R
+
+
+class speculative:
+    """Context manager used by the autograd bridges in training mode: inside it the forward entry points do NOT
+    synchronise with the host (the one sync of the reference API, `num_rendered` being a Python int, is what
+    serialises host and device twice per training iteration).  The binning buffer is provisioned from the instance
+    count of the previous call with the same shape (+20 %), the status word travels to pinned host memory behind an
+    event, and the check happens in the backward.  Disabled by R2X_SPECULATIVE=0, by debug=True, under no_grad, and
+    for the first call of a shape (no hint yet)."""
+
+    _tls = threading.local()
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on) and os.environ.get("R2X_SPECULATIVE", "1") != "0"
+
+    def __enter__(self):
+        self.prev = getattr(self._tls, "on", False)
+        self._tls.on = self.on
+        return self
+
+    def __exit__(self, *exc):
+        self._tls.on = self.prev
+        return False
+
+    @classmethod
+    def active(cls) -> bool:
+        return bool(getattr(cls._tls, "on", False))
 
 
 def _carved_capacity(binning: torch.Tensor, R) -> int:
     """Instance count the binning buffer was carved for (what the backward must carve with)."""
     return int(getattr(R, "capacity", R))
+
+
+def _pending(status, cap, key, dev) -> NumRendered:
+    """Ship the device status word {R, overflow} to pinned host memory behind an event (no host wait)."""
+    host = _Workspace.pinned_status()
+    host.copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return NumRendered(cap, cap, (host, ev, key))
 
 
 def _status_pair(dev):
@@ -137,6 +211,9 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
             check(rc, "r2x_raster_forward")
             return NumRendered(nr.value), out_color, radii, geom, alloc.tensor, img
         cap = _Workspace.capacity(key, P, 12)
+        spec = speculative.active() and key in _Workspace.hints
+        if spec:    # generous: an overflow needs the instance count to double between two calls of this shape
+            cap = _Workspace._round(max(2 * cap, 12 * P))
         while True:
             binning = torch.empty(lib.r2x_binning_bytes(cap), **u8)
             rc = lib.r2x_raster_forward_async(
@@ -145,6 +222,8 @@ def rasterize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov
                 int(bool(prefiltered)), int(mode), out_color.data_ptr(), _ptr(radii), geom.data_ptr(), img.data_ptr(),
                 binning.data_ptr(), cap, status.data_ptr())
             check(rc, "r2x_raster_forward_async")
+            if spec:
+                return (_pending(status, cap, key, dev), out_color, radii, geom, binning, img)
             R, overflow = status.tolist()      # the one host synchronisation of the call
             _Workspace.update(key, R)
             if not overflow:
@@ -184,6 +263,8 @@ def rasterize_gaussians_backward(means3D, radii, scales, rotations, scale_modifi
         g_mean2D = torch.empty((P, 3), **opts); g_op = torch.empty((P, 1), **opts); g_mu = torch.empty((P, 1), **opts)
         g_mean3D = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
         g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        if getattr(R, "pending", None) is not None:
+            R.resolve()                         # raises CapacityOverflow if the speculative forward did not fit
         R = _carved_capacity(binningBuffer, R)
         scratch = torch.empty(lib.r2x_raster_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
         rc = lib.r2x_raster_backward(
@@ -246,12 +327,17 @@ def voxelize_gaussians(means3D, opacity, scales, rotations, scale_modifier, cov3
         key = ("voxel", dev.index, P, nx, ny, nz, round(float(sVoxel_x) / nx, 6))
         status = _status_pair(dev)
         cap = _Workspace.capacity(key, P, 8)
+        spec = speculative.active() and key in _Workspace.hints
+        if spec:    # (random TV crops see very different instance counts: keep at least 8 per Gaussian)
+            cap = _Workspace._round(max(2 * cap, 8 * P))
         while True:
             binning = torch.empty(lib.r2x_binning_bytes(cap), **u8)
             rc = lib.r2x_voxel_forward_async(stream, P, *grid_args, *in_args, vol.data_ptr(), _ptr(rx), _ptr(ry),
                                              _ptr(rz), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), cap,
                                              status.data_ptr())
             check(rc, "r2x_voxel_forward_async")
+            if spec:
+                return (_pending(status, cap, key, dev), vol, rx, ry, rz, geom, binning, img)
             R, overflow = status.tolist()
             _Workspace.update(key, R)
             if not overflow:
@@ -275,6 +361,8 @@ def voxelize_gaussians_backward(means3D, radii_x, radii_y, radii_z, scales, rota
         opts = dict(dtype=torch.float32, device=dev)
         g_op = torch.empty((P, 1), **opts); g_mean = torch.empty((P, 3), **opts); g_cov = torch.empty((P, 6), **opts)
         g_scale = torch.empty((P, 3), **opts); g_rot = torch.empty((P, 4), **opts)
+        if getattr(R, "pending", None) is not None:
+            R.resolve()
         R = _carved_capacity(binningBuffer, R)
         scratch = torch.empty(lib.r2x_voxel_bwd_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
         rc = lib.r2x_voxel_backward(

@@ -52,6 +52,9 @@ PROTOTYPES = {
     "r2x_tv3d_scratch_bytes": (_sz, [_i, _i, _i]),
     "r2x_tv3d_loss": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz]),
     "r2x_adam_step": (_i, [_vp, _i, _vp, C.c_double, C.c_double, C.c_double, _ll]),
+    "r2x_mask_select_scratch_bytes": (_sz, [_i]),
+    "r2x_mask_select": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz]),
+    "r2x_gather_rows": (_i, [_vp, _i, _vp, _vp, _ll]),
     "r2x_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "r2x_peer_free": (_i, [_vp]),
     "r2x_ipc_export": (_i, [_vp, _vp]),
@@ -60,6 +63,11 @@ PROTOTYPES = {
     "r2x_peer_allreduce_sum": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp]),
     "r2x_peer_allreduce_sum_t": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp, _ll]),
 }
+
+
+class GatherDesc(C.Structure):
+    """Mirror of `r2x_gather_desc` (include/r2x.h)."""
+    _fields_ = [("src0", C.c_void_p), ("src1", C.c_void_p), ("dst", C.c_void_p), ("n0", C.c_longlong), ("width", C.c_int)]
 
 
 class AdamGroup(C.Structure):

@@ -148,6 +148,17 @@ int debug_sync(cudaStream_t st, int debug, const char* stage) {
     } while (0)
 
 // ---- export kernels ---------------------------------------------------------------------------
+// tile ranges in the reference's convention: an empty tile reads (0, 0) (the reference zero-fills `ranges` and only
+// writes the non-empty ones, RAS/rasterizer_impl.cu:308-321); direct binning keeps (start, start) internally
+__global__ void export_ranges_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const uint2 r = ranges[t];
+    const bool empty = (r.x == r.y);
+    out[2 * (size_t)t] = empty ? 0u : r.x;
+    out[2 * (size_t)t + 1] = empty ? 0u : r.y;
+}
+
 __global__ void raster_export_geom_kernel(int P, RasterGeom geom, float* means2D, float* depths, float* conic_opacity,
                                           float* mus, uint32_t* tiles_touched, uint32_t* point_offsets) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -476,7 +487,7 @@ int r2x_raster_export(void* stream, int P, int W, int H, long long R, const void
     raster_export_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, s.geom, means2D, depths, conic_opacity, mus,
                                                                 tiles_touched, point_offsets);
     const int tiles = s.geom.gx * s.geom.gy;
-    if (ranges) R2X_CUDA_OK(cudaMemcpyAsync(ranges, (const void*)al((size_t)image_buf), sizeof(uint2) * tiles, cudaMemcpyDeviceToDevice, st));
+    if (ranges) export_ranges_kernel<<<(tiles + 255) / 256, 256, 0, st>>>(tiles, (const uint2*)al((size_t)image_buf), ranges);
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok(tiles)) {
@@ -554,7 +565,7 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     voxel_export_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, s.geom, means3D_norm, depths, conic_opacity,
                                                                tiles_touched, point_offsets);
     const size_t tiles = (size_t)((nx + 7) / 8) * ((ny + 7) / 8) * ((nz + 7) / 8);
-    if (ranges) R2X_CUDA_OK(cudaMemcpyAsync(ranges, (const void*)al((size_t)image_buf), sizeof(uint2) * tiles, cudaMemcpyDeviceToDevice, st));
+    if (ranges) export_ranges_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>((int)tiles, (const uint2*)al((size_t)image_buf), ranges);
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
         if (direct_ok((int)tiles)) {

@@ -73,11 +73,12 @@ int reset_plan_counter(cudaStream_t st, const TilePlan& plan, int which);
 
 // chunk `chunk` of `nch` equal slices of the tile list [r.x, r.y)
 __device__ __forceinline__ void plan_slice(const uint2 r, int chunk, int nch, uint32_t& begin, int& n) {
+    // len = q nch + rem: the first `rem` slices hold q + 1 instances, the others q (one 32-bit division)
     const uint32_t len = r.y - r.x;
-    const uint32_t lo = (uint32_t)(((unsigned long long)len * (uint32_t)chunk) / (uint32_t)nch);
-    const uint32_t hi = (uint32_t)(((unsigned long long)len * (uint32_t)(chunk + 1)) / (uint32_t)nch);
-    begin = r.x + lo;
-    n = (int)(hi - lo);
+    const uint32_t q = len / (uint32_t)nch, rem = len - q * (uint32_t)nch;
+    const uint32_t c = (uint32_t)chunk;
+    begin = r.x + q * c + (c < rem ? c : rem);
+    n = (int)(q + (c < rem ? 1u : 0u));
 }
 
 __device__ __forceinline__ void plan_decode(const TilePlan& pl, const uint2* __restrict__ ranges, uint32_t item,

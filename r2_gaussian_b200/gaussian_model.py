@@ -6,10 +6,13 @@ split / prune rules) so the reference's `train.py` / `test.py` can drive it unch
 
 * `distCUDA2` comes from this repository's grid-hash kernel (`r2_gaussian_b200.simple_knn`);
 * the optimizer is `FusedAdam` (one launch per step for all four groups, same state layout as torch's Adam);
-* densification rebuilds every per-Gaussian tensor (4 parameters, 8 Adam moments, `max_radii2D`) ONCE: clone,
-  split and all prune rules are evaluated into one row-selection, then each tensor is gathered once -- the
-  reference cats and boolean-masks every tensor up to three times per call and empties the allocator cache.
-  Row order of the result equals the reference's ([survivors | clones | split children], then pruned).
+* densification rebuilds every per-Gaussian tensor (4 parameters, 8 Adam moments, `max_radii2D`, statistics) ONCE
+  and on the device: clone, split and all prune rules are evaluated into one row selection (`compact.select_rows`:
+  mask -> scan -> stable index list, the count stays on the device) and ONE launch gathers all tensors through it
+  (`compact.gather_rows`).  No boolean-mask indexing anywhere (each `t[mask]` of the reference is a nonzero() with a
+  host synchronisation); a densification step costs two small host reads (how many clones / splits, how many
+  survivors) instead of ~30.  Row order of the result equals the reference's ([survivors | clones | split
+  children], then pruned), parameters / moments / RNG stream bit-equal.
 """
 from __future__ import annotations
 
@@ -20,6 +23,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import compact
 from .gaussian_utils import (build_rotation, build_scaling_rotation, get_expon_lr_func, inverse_sigmoid,
                              inverse_softplus, strip_symmetric)
 from .optim import FusedAdam
@@ -188,43 +192,61 @@ class GaussianModel:
                 out[name] = self._swap_param(group, tensor, lambda m: torch.zeros_like(tensor))
         return out
 
-    def _gather_rows(self, select, extra=None):
-        """new = cat([old, extra[name]])[select] for every parameter, its Adam moments (zeros for the extra
-        rows) and return the new parameters by group name."""
-        out = {}
+    def _gather_rows(self, select, extra=None, nsel=None, stats=()):
+        """new = cat([old, extra[name]])[select] for every parameter and its Adam moments (zeros for the extra rows),
+        plus the `stats` tensors ((old, extra-or-None) pairs), all in ONE launch of r2x_gather_rows.  `select`: int32
+        index list on the device (first `nsel` entries valid), a bool mask (converted on the device), or None =
+        everything.  Returns ({group name: new Parameter}, [gathered stats], nsel)."""
+        n_old = int(self._xyz.shape[0])
+        n_extra = 0 if extra is None else int(extra["xyz"].shape[0])
+        if select is None:
+            nsel = n_old + n_extra
+        elif select.dtype in (torch.bool, torch.uint8):
+            select, count = compact.select_rows(select)
+            nsel = compact.read_counts(count)[0]
+        specs, slots = [], []
         for group in self.optimizer.param_groups:
             name = group["name"]
             old = group["params"][0]
             add = None if extra is None else extra[name]
-
-            def rows(t, pad_zero, add=add):
-                if add is not None:
-                    t = torch.cat((t, torch.zeros_like(add) if pad_zero else add), dim=0)
-                return t if select is None else t[select]
-
-            out[name] = self._swap_param(group, rows(old.detach(), False), lambda m: rows(m, True))
-        return out
+            st = self.optimizer.state.get(old, None)
+            specs.append((old, add))
+            if st is not None:
+                specs.append((st["exp_avg"], None))
+                specs.append((st["exp_avg_sq"], None))
+            slots.append((group, name, old, st))
+        specs += list(stats)
+        got = compact.gather_rows(specs, select, nsel)
+        out, k = {}, 0
+        for group, name, old, st in slots:
+            new = nn.Parameter(got[k].requires_grad_(True)); k += 1
+            self.optimizer.state.pop(old, None)
+            group["params"][0] = new
+            if st is not None:
+                st["exp_avg"], st["exp_avg_sq"] = got[k], got[k + 1]; k += 2
+                self.optimizer.state[new] = st
+            out[name] = new
+        return out, got[k:], nsel
 
     def _adopt(self, params):
         for name, attr in _GROUPS:
             setattr(self, attr, params[name])
 
     def _prune_optimizer(self, mask):
-        return self._gather_rows(mask)
+        return self._gather_rows(mask)[0]
 
     def cat_tensors_to_optimizer(self, tensors_dict):
-        return self._gather_rows(None, tensors_dict)
+        return self._gather_rows(None, tensors_dict)[0]
 
     def prune_points(self, mask):
-        keep = ~mask
-        self._adopt(self._gather_rows(keep))
-        self.xyz_gradient_accum = self.xyz_gradient_accum[keep]
-        self.denom = self.denom[keep]
-        self.max_radii2D = self.max_radii2D[keep]
+        params, (accum, denom, radii), _ = self._gather_rows(
+            ~mask, stats=[(self.xyz_gradient_accum, None), (self.denom, None), (self.max_radii2D, None)])
+        self._adopt(params)
+        self.xyz_gradient_accum, self.denom, self.max_radii2D = accum, denom, radii
 
     def densification_postfix(self, new_xyz, new_densities, new_scaling, new_rotation, new_max_radii2D):
         extra = {"xyz": new_xyz, "density": new_densities, "scaling": new_scaling, "rotation": new_rotation}
-        self._adopt(self._gather_rows(None, extra))
+        self._adopt(self._gather_rows(None, extra)[0])
         n = self.get_xyz.shape[0]
         self.xyz_gradient_accum = torch.zeros((n, 1), device="cuda")
         self.denom = torch.zeros((n, 1), device="cuda")
@@ -235,17 +257,21 @@ class GaussianModel:
         self._density = self.replace_tensor_to_optimizer(self.density_inverse_activation(capped), "density")["density"]
 
     # ------------------------------------------------------------------ adaptive control
-    def _split_children(self, mask, N):
+    def _rows(self, t, rows):
+        """t[rows] for a bool mask (reference-style call) or an int index list (device-side selection)."""
+        return t[rows] if rows.dtype == torch.bool else t.index_select(0, rows)
+
+    def _split_children(self, rows, N):
         """N children per selected Gaussian: positions drawn from the parent (`:430-455`), scale / (0.8 N),
-        density / N."""
-        scale = self.get_scaling[mask].repeat(N, 1)
+        density / N.  `rows`: bool mask or int index list of the parents."""
+        scale = self._rows(self.get_scaling, rows).repeat(N, 1)
         offsets = torch.normal(mean=torch.zeros((scale.size(0), 3), device="cuda"), std=scale)
-        frames = build_rotation(self._rotation[mask]).repeat(N, 1, 1)
-        xyz = torch.bmm(frames, offsets.unsqueeze(-1)).squeeze(-1) + self.get_xyz[mask].repeat(N, 1)
+        frames = build_rotation(self._rows(self._rotation, rows)).repeat(N, 1, 1)
+        xyz = torch.bmm(frames, offsets.unsqueeze(-1)).squeeze(-1) + self._rows(self.get_xyz, rows).repeat(N, 1)
         return {"xyz": xyz,
-                "density": self.density_inverse_activation(self.get_density[mask].repeat(N, 1) * (1 / N)),
+                "density": self.density_inverse_activation(self._rows(self.get_density, rows).repeat(N, 1) * (1 / N)),
                 "scaling": self.scaling_inverse_activation(scale / (0.8 * N)),
-                "rotation": self._rotation[mask].repeat(N, 1)}, self.max_radii2D[mask].repeat(N)
+                "rotation": self._rows(self._rotation, rows).repeat(N, 1)}, self._rows(self.max_radii2D, rows).repeat(N)
 
     def densify_and_split(self, grads, grad_threshold, densify_scale_threshold, N=2):
         n = self.get_xyz.shape[0]
@@ -266,53 +292,66 @@ class GaussianModel:
 
     def densify_and_prune(self, max_grad, min_density, max_screen_size, max_scale, max_num_gaussians,
                           densify_scale_threshold, bbox=None):
-        """Clone + split + every prune rule (`:503-550`) with ONE rebuild of the per-Gaussian storage."""
+        """Clone + split + every prune rule (`:503-550`) with ONE rebuild of the per-Gaussian storage, selection and
+        compaction on the device: two small host reads per call (clone / split counts, survivor count)."""
         grads = self.xyz_gradient_accum / self.denom
-        grads[grads.isnan()] = 0.0
+        grads = torch.where(grads.isnan(), torch.zeros_like(grads), grads)
         n0 = grads.shape[0]
         extra, extra_radii, drop_parent = None, None, None
         with torch.no_grad():
+            density_old = self._density.detach()
             if densify_scale_threshold and (not max_num_gaussians or n0 < max_num_gaussians):
                 max_s = torch.max(self.get_scaling, dim=1).values
                 hot = torch.norm(grads, dim=-1) >= max_grad
                 clone_m = hot & (max_s <= densify_scale_threshold)
                 split_m = hot & (max_s > densify_scale_threshold)
-                # clones: twin rows with half the density; the originals are halved in place
-                halved = self.density_inverse_activation(self.get_density[clone_m] * 0.5)
-                twins = {"xyz": self._xyz[clone_m], "density": halved, "scaling": self._scaling[clone_m],
-                         "rotation": self._rotation[clone_m]}
-                twin_radii = self.max_radii2D[clone_m]
-                self._density[clone_m] = halved
+                ci, cn = compact.select_rows(clone_m)
+                si, sn = compact.select_rows(split_m)
+                n_clone, n_split = compact.read_counts(cn, sn)                  # host read 1 of 2
+                ci, si = ci[:n_clone].long(), si[:n_split].long()
+                # clones: twin rows with half the density; the originals are halved too (`:493`)
+                halved = self.density_inverse_activation(self.get_density * 0.5)
+                twins = {"xyz": self._xyz.detach().index_select(0, ci), "density": halved.index_select(0, ci),
+                         "scaling": self._scaling.detach().index_select(0, ci),
+                         "rotation": self._rotation.detach().index_select(0, ci)}
+                twin_radii = self.max_radii2D.index_select(0, ci)
+                density_old = torch.where(clone_m.unsqueeze(-1), halved, density_old)
                 # split children are drawn from the parents (which the clone step did not touch: disjoint masks)
-                children, child_radii = self._split_children(split_m, 2)
+                children, child_radii = self._split_children(si, 2)
                 extra = {k: torch.cat((twins[k], children[k]), dim=0) for k in twins}
                 extra_radii = torch.cat((twin_radii, child_radii), dim=-1)
                 drop_parent = split_m
             # candidate rows after densification: [old | twins | children]
             cat = (lambda old, new: old if new is None else torch.cat((old, new), dim=0))
-            xyz = cat(self._xyz, None if extra is None else extra["xyz"])
-            dens = self.density_activation(cat(self._density, None if extra is None else extra["density"]))
-            scal = self.scaling_activation(cat(self._scaling, None if extra is None else extra["scaling"]))
+            xyz = cat(self._xyz.detach(), None if extra is None else extra["xyz"])
+            dens = self.density_activation(cat(density_old, None if extra is None else extra["density"]))
+            scal = self.scaling_activation(cat(self._scaling.detach(), None if extra is None else extra["scaling"]))
             radii = cat(self.max_radii2D, extra_radii)
             drop = (dens < min_density).squeeze(-1)
             if drop_parent is not None:
-                drop[:n0] |= drop_parent
+                drop = drop | cat(drop_parent, torch.zeros(drop.shape[0] - n0, dtype=torch.bool, device=drop.device))
             if bbox is not None:
-                drop |= ((xyz < bbox[0].to(xyz.device)) | (xyz > bbox[1].to(xyz.device))).any(dim=1)
+                drop = drop | ((xyz < bbox[0].to(xyz.device)) | (xyz > bbox[1].to(xyz.device))).any(dim=1)
             if max_screen_size:
-                drop |= radii > max_screen_size
+                drop = drop | (radii > max_screen_size)
             if max_scale:
-                drop |= scal.max(dim=1).values > max_scale
-            keep = torch.nonzero(~drop).squeeze(-1)          # the one host round trip of this call
-            self._adopt(self._gather_rows(keep, extra))
-            n = int(keep.numel())
-            self.max_radii2D = radii[keep]
+                drop = drop | (scal.max(dim=1).values > max_scale)
+            keep, kn = compact.select_rows(~drop)
+            n = compact.read_counts(kn)[0]                                      # host read 2 of 2
+            # the originals of the clones carry their halved density into the gather
+            if density_old is not self._density:
+                self._density.data = density_old if density_old.is_contiguous() else density_old.contiguous()
+            stats = [(self.max_radii2D, extra_radii)]
+            if extra is None:
+                stats += [(self.xyz_gradient_accum, None), (self.denom, None)]
+            params, got, _ = self._gather_rows(keep, extra, nsel=n, stats=stats)
+            self._adopt(params)
+            self.max_radii2D = got[0]
             if extra is not None:
                 self.xyz_gradient_accum = torch.zeros((n, 1), device="cuda")
                 self.denom = torch.zeros((n, 1), device="cuda")
             else:
-                self.xyz_gradient_accum = self.xyz_gradient_accum[keep]
-                self.denom = self.denom[keep]
+                self.xyz_gradient_accum, self.denom = got[1], got[2]
         return grads
 
     def add_densification_stats(self, viewspace_point_tensor, update_filter):

@@ -41,8 +41,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         native_args = (means3D, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.viewmatrix,
                        s.projmatrix, s.tanfovx, s.tanfovy, s.image_height, s.image_width, s.campos, s.prefiltered,
                        s.mode, s.debug)
-        num_rendered, color, radii, geom, binning, img = call_with_snapshot(
-            _C.rasterize_gaussians, native_args, s.debug, "snapshot_fw.dump", "forward")
+        # training mode (some input needs a gradient): no host synchronisation in the forward, the instance-capacity
+        # check is deferred to the backward (_C.speculative)
+        with _C.speculative(any(ctx.needs_input_grad) and not s.debug):
+            num_rendered, color, radii, geom, binning, img = call_with_snapshot(
+                _C.rasterize_gaussians, native_args, s.debug, "snapshot_fw.dump", "forward")
         ctx.raster_settings = s
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(means3D, scales, rotations, cov3Ds_precomp, radii, geom, binning, img)

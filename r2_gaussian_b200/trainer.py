@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from . import losses
+from ._C import CapacityOverflow
 from .dataset import Scene
 from .gaussian_model import GaussianModel
 from .metrics import metric_proj, metric_vol
@@ -192,7 +193,18 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
             centre = (bbox_cpu[0] + tv_s / 2) + (bbox_cpu[1] - tv_s - bbox_cpu[0]) * torch.rand(3)
             vol = query(gaussians, centre, tv_n, tv_s, pipe)["vol"]
             total = total + opt.lambda_tv * losses.tv_3d_loss(vol, reduction="mean")
-        total.backward()
+        try:
+            total.backward()
+        except CapacityOverflow:
+            # a speculative forward (no host sync) ran out of instance capacity: its image was all zeros and this
+            # step's gradients are void.  The capacity hint has been raised; redo the step with the same camera.
+            gaussians.optimizer.zero_grad(set_to_none=True)
+            pkg = render(cam, gaussians, pipe)
+            total = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)["total"]
+            if use_tv:
+                total = total + opt.lambda_tv * losses.tv_3d_loss(query(gaussians, centre, tv_n, tv_s, pipe)["vol"],
+                                                                  reduction="mean")
+            total.backward()
 
         with torch.no_grad():
             gaussians.update_max_radii(pkg["radii"], pkg["visibility_filter"])

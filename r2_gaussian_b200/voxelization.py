@@ -41,8 +41,9 @@ class _VoxelizeGaussians(torch.autograd.Function):
         native_args = (means3D, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp, s.nVoxel_x,
                        s.nVoxel_y, s.nVoxel_z, s.sVoxel_x, s.sVoxel_y, s.sVoxel_z, s.center_x, s.center_y,
                        s.center_z, s.prefiltered, s.debug)
-        num_rendered, vol, rx, ry, rz, geom, binning, img = call_with_snapshot(
-            _C.voxelize_gaussians, native_args, s.debug, "snapshot_fw.dump", "forward")
+        with _C.speculative(any(ctx.needs_input_grad) and not s.debug):
+            num_rendered, vol, rx, ry, rz, geom, binning, img = call_with_snapshot(
+                _C.voxelize_gaussians, native_args, s.debug, "snapshot_fw.dump", "forward")
         ctx.voxel_settings = s
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(means3D, scales, rotations, cov3Ds_precomp, rx, ry, rz, geom, binning, img)

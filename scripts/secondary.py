@@ -173,7 +173,10 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
         scaling_lr_init=5e-3, scaling_lr_final=5e-4, scaling_lr_max_steps=30000,
         rotation_lr_init=1e-3, rotation_lr_final=1e-4, rotation_lr_max_steps=30000)
     gm = GaussianModel((0.001, 1.0))
-    gm.create_from_pcd(cloud.means, np.maximum(cloud.density, 1e-3), 1.0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):      # create_from_pcd prints like the reference; bench.py prints ONE JSON line
+        gm.create_from_pcd(cloud.means, np.maximum(cloud.density, 1e-3), 1.0)
     gm.training_setup(opt_args)
     pipe = types.SimpleNamespace(compute_cov3D_python=False, debug=False)
     with torch.no_grad():

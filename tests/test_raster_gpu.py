@@ -163,3 +163,44 @@ def test_host_projector_pipeline_matches_direct_forward():
     a, b, c, v = hv[3]
     got = hp.project(hm, hd, hs, hr, a, b, c, v.tanfovx, v.tanfovy, v.mode, outs[0])
     assert torch.equal(got, want[3])
+
+
+def test_speculative_training_forward_defers_the_capacity_check():
+    """Training mode (inputs require grad): the forward does not synchronise; num_rendered is an upper bound that the
+    backward resolves.  Results equal the synchronous path; a forward whose instance count more than doubled since the
+    previous call of the same shape raises CapacityOverflow in the backward, and repeating the step succeeds."""
+    import torch
+    from r2_gaussian_b200 import _C
+    from r2_gaussian_b200.rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+    cloud, view = util.case("cone_trained_small")
+
+    def run(c):
+        t = util.to_torch(c, view, requires_grad=True)
+        m2 = torch.zeros_like(t["means"], requires_grad=True)
+        s = GaussianRasterizationSettings(view.image_height, view.image_width, view.tanfovx, view.tanfovy, 1.0, t["view"],
+                                          t["proj"], t["campos"], False, view.mode, False)
+        img, radii = GaussianRasterizer(s)(t["means"], m2, t["dens"], t["scales"], t["rots"])
+        return t, img
+
+    key = ("raster", 0, cloud.P, view.image_width, view.image_height)
+    _C._Workspace.hints.pop(key, None)
+    t1, img1 = run(cloud)                          # first call of the shape: synchronous, sets the hint
+    assert key in _C._Workspace.hints
+    img1.sum().backward()
+    t2, img2 = run(cloud)                          # second call: speculative
+    assert torch.equal(img1, img2)
+    img2.sum().backward()
+    for k in ("means", "dens", "scales", "rots"):
+        assert torch.equal(t1[k].grad, t2[k].grad), k
+    # same shape, 6x larger Gaussians: far more than twice the instances -> overflow is reported by the backward
+    big = type(cloud)(cloud.means, np.clip(cloud.scales * 6.0, 0, 0.9).astype(np.float32), cloud.rotations, cloud.density)
+    ref = util.oracle_raster_forward(big, view)
+    assert ref["R"] > 2.5 * int(_C._Workspace.hints[key]) and ref["R"] > 12 * cloud.P
+    t3, img3 = run(big)
+    with pytest.raises(_C.CapacityOverflow):
+        img3.sum().backward()
+    t4, img4 = run(big)                            # the hint was raised: the repeated step fits
+    img4.sum().backward()
+    err = np.abs(img4[0].detach().cpu().numpy().astype(np.float64) - ref["image"]).max()
+    assert err <= 1e-5 * np.abs(ref["image"]).max() + 1e-7
