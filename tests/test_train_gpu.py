@@ -399,3 +399,96 @@ def test_fused_losses_against_reference_golden_vectors(tag):
             assert abs(t.item() - want) <= 2e-6 * max(1.0, abs(want))
             gw = G[f"tv_{tag}_{red}_grad"]
             assert np.abs(v.grad.cpu().numpy() - gw).max() <= 1e-6 * max(1.0, np.abs(gw).max())
+
+
+def _reference_gaussian_model():
+    """The reference's own GaussianModel class (r2_gaussian/gaussian/gaussian_model.py), imported unchanged from the
+    copy scripts/run_reference_drivers.py --prepare puts under baseline/_ref (with the import placeholders of
+    scripts/ref_shims for plyfile & co. and this repository's simple_knn)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "r2_gaussian")):
+        pytest.fail("baseline/_ref is empty: run `python scripts/run_reference_drivers.py --prepare` in the build container")
+    for p in (os.path.join(root, "scripts", "ref_shims"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    return importlib.import_module("r2_gaussian.gaussian.gaussian_model").GaussianModel
+
+
+@pytest.mark.parametrize("max_num", [None, 10])
+def test_densify_and_prune_bit_equal_to_the_reference_class(max_num):
+    """Device-side compaction (r2x_mask_select + r2x_gather_rows) against the reference's cat / boolean-mask sequence,
+    run live from the reference's own class: parameters, both Adam moments, max_radii2D, statistics, row order and the
+    CUDA RNG stream are bit-identical (max_num=10: the densification branch is skipped, prune only)."""
+    RefModel = _reference_gaussian_model()
+    groups = (("xyz", "_xyz"), ("density", "_density"), ("scaling", "_scaling"), ("rotation", "_rotation"))
+    gm, xyz, dens = _make_model(n=6000, seed=5)
+    torch.manual_seed(1)
+    for _ in range(3):      # a few optimizer steps so that the Adam moments are non-trivial
+        for _, attr in groups:
+            p = getattr(gm, attr)
+            p.grad = torch.randn_like(p) * 1e-2
+        gm.optimizer.step()
+    n = gm.get_xyz.shape[0]
+    gm.max_radii2D = torch.rand(n, device="cuda") * 40
+    gm.xyz_gradient_accum = torch.rand(n, 1, device="cuda") * 3e-3
+    gm.denom = torch.randint(0, 4, (n, 1), device="cuda").float()
+    with torch.no_grad():
+        gm._scaling[: n // 2] += 2.0
+        gm._density[::17] = -9.0
+    # the reference model in exactly the same state
+    ref = RefModel(np.array(gm.scale_bound))
+    ref.create_from_pcd(xyz, dens, 1.0)
+    ref.training_setup(_opt_args())
+    with torch.no_grad():
+        for name, attr in groups:
+            getattr(ref, attr).copy_(getattr(gm, attr))
+    for g_ref, (name, attr) in zip(ref.optimizer.param_groups, groups):
+        assert g_ref["name"] == name
+        src = gm.optimizer.state[getattr(gm, attr)]
+        ref.optimizer.state[g_ref["params"][0]] = {"step": src["step"].clone(), "exp_avg": src["exp_avg"].clone(),
+                                                   "exp_avg_sq": src["exp_avg_sq"].clone()}
+    ref.max_radii2D = gm.max_radii2D.clone()
+    ref.xyz_gradient_accum = gm.xyz_gradient_accum.clone()
+    ref.denom = gm.denom.clone()
+    bbox = torch.tensor([[-0.75, -0.75, -0.75], [0.75, 0.75, 0.75]], device="cuda")
+    args = (5e-4, 1e-3, 35.0, 0.3, max_num, 0.01, bbox)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        g_ref = ref.densify_and_prune(*args)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        g_our = gm.densify_and_prune(*args)
+    assert torch.equal(g_our, g_ref)
+    assert gm.get_xyz.shape[0] == ref.get_xyz.shape[0] and gm.get_xyz.shape[0] != n
+    for name, attr in groups:
+        a, b = getattr(gm, attr), getattr(ref, attr)
+        assert torch.equal(a.detach(), b.detach()), name
+        sa, sb = gm.optimizer.state[a], ref.optimizer.state[b]
+        assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"]), name
+    assert torch.equal(gm.max_radii2D, ref.max_radii2D)
+    assert torch.equal(gm.xyz_gradient_accum, ref.xyz_gradient_accum) and torch.equal(gm.denom, ref.denom)
+    # and the same stream of random numbers has been consumed
+    assert torch.equal(torch.rand(4, device="cuda"), torch.rand(4, device="cuda")) is False
+    torch.manual_seed(7); x = torch.rand(3, device="cuda")
+    torch.manual_seed(7); assert torch.equal(x, torch.rand(3, device="cuda"))
+
+
+def test_select_and_gather_rows_against_torch_indexing():
+    from r2_gaussian_b200 import compact
+    g = torch.Generator("cuda").manual_seed(3)
+    for n in (0, 1, 5, 1000, 70001):
+        mask = torch.rand(n, device="cuda", generator=g) < 0.37
+        idx, cnt = compact.select_rows(mask)
+        k = compact.read_counts(cnt)[0]
+        want = torch.nonzero(mask).squeeze(-1)
+        assert k == want.numel() and torch.equal(idx[:k].long(), want)
+        a = torch.randn(n, 3, device="cuda", generator=g); b = torch.randn(n, device="cuda", generator=g)
+        extra = torch.randn(7, 3, device="cuda", generator=g)
+        sel = torch.cat((idx[:k], torch.arange(n, n + 7, device="cuda", dtype=torch.int32)))
+        out = compact.gather_rows([(a, extra), (b, None), (a, None)], sel, k + 7)
+        assert torch.equal(out[0], torch.cat((a, extra))[sel.long()])
+        assert torch.equal(out[1], torch.cat((b, torch.zeros(7, device="cuda")))[sel.long()])
+        assert torch.equal(out[2], torch.cat((a, torch.zeros(7, 3, device="cuda")))[sel.long()])
