@@ -458,9 +458,11 @@ def test_densify_and_prune_bit_equal_to_the_reference_class(max_num):
     torch.manual_seed(123)
     with torch.no_grad():
         g_ref = ref.densify_and_prune(*args)
+    rng_ref = torch.cuda.get_rng_state()
     torch.manual_seed(123)
     with torch.no_grad():
         g_our = gm.densify_and_prune(*args)
+    assert torch.equal(torch.cuda.get_rng_state(), rng_ref)      # the same stream of random numbers has been consumed
     assert torch.equal(g_our, g_ref)
     assert gm.get_xyz.shape[0] == ref.get_xyz.shape[0] and gm.get_xyz.shape[0] != n
     for name, attr in groups:
@@ -470,10 +472,6 @@ def test_densify_and_prune_bit_equal_to_the_reference_class(max_num):
         assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"]), name
     assert torch.equal(gm.max_radii2D, ref.max_radii2D)
     assert torch.equal(gm.xyz_gradient_accum, ref.xyz_gradient_accum) and torch.equal(gm.denom, ref.denom)
-    # and the same stream of random numbers has been consumed
-    assert torch.equal(torch.rand(4, device="cuda"), torch.rand(4, device="cuda")) is False
-    torch.manual_seed(7); x = torch.rand(3, device="cuda")
-    torch.manual_seed(7); assert torch.equal(x, torch.rand(3, device="cuda"))
 
 
 def test_select_and_gather_rows_against_torch_indexing():
