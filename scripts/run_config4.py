@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=600)
     ap.add_argument("--init", type=int, default=300000)
     ap.add_argument("--det", type=int, default=256)
-    ap.add_argument("--vox", type=int, default=128)
+    ap.add_argument("--vox", type=int, default=160)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config4"))
     ap.add_argument("--peer_exchange", action="store_true")
     a = ap.parse_args()
