@@ -155,10 +155,23 @@ def test_raster_cov3D_precomp_path():
 
 
 def test_voxel_cov3D_precomp_path():
+    """Forward against the reference.  The reference's voxelizer backward cannot run with cov3D_precomp (it needs
+    `scales` for the radius, VOX/forward.cu:137, and then differentiates through `rotations`, which are absent:
+    VOX/backward.cu:201-211 dereferences a null pointer), so the gradients are checked against the CPU oracle."""
     cloud = cloud_of(20_000, "trained")
     view = scene.make_view(scene.cone_beam_scanner(64, 64), 0.0)
     cov = _precomputed_cov(cloud, view)
-    check_voxel(cloud, (64, 64, 64), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0), cov3D_precomp=cov)
+    grid = ((64, 64, 64), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0))
+    ours, _ = check_voxel(cloud, *grid, backward=False, cov3D_precomp=cov)
+    ours_s, _ = check_voxel(cloud, *grid, backward=False)
+    np.testing.assert_array_equal(ours["vol"].view(np.uint32), ours_s["vol"].view(np.uint32))
+    dL = np.random.RandomState(6).randn(*grid[0]).astype(np.float32)
+    g = util.ours_voxel_backward(cloud, *grid, ours, dL)
+    orc = util.oracle_voxel_forward(cloud, *grid, cov3D_precomp=cov)
+    from oracle import r2_oracle as o
+    go = o.voxel_backward(orc, cloud.scales, None, grid[0], grid[1], dL, cov3D_precomp=cov)
+    util.assert_grads_close(g, go, ["dL_dopacity", "dL_dmean3D", "dL_dcov3D"])
+    assert not g["dL_dscale"].any() and not g["dL_drot"].any()
 
 
 def test_debug_true_synchronous_abi():
