@@ -404,7 +404,7 @@ def run_ours(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_render * 1e3, "peak_source": peak_src,
                 "pair_evals_per_launch": pairs, "pair_evals_per_s": pairs / t_render,
-                "timed": "r2x_raster_render_only = plan_kernel (queue reset, a few us) + raster_render_kernel, CUDA events, L2 flushed",
+                "timed": "r2x_raster_render_only = two small memsets (queue head, arrival counters) + the render kernel, CUDA events, L2 flushed",
                 "note": "kernel is FP32-issue-bound (multiplicative forward differences: ~5 issue slots and 0.5 "
                         "MUFU.EX2 per pixel-Gaussian pair), not HBM-bound; see DESIGN.md section 5"}
     try:   # the bound that does apply: one MUFU.EX2 per pair; 15.85 ex2/clk/SM measured (scripts/micro/mufu_rate.cu)

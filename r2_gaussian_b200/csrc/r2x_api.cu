@@ -424,7 +424,9 @@ int r2x_raster_render_only(void* stream, int P, int W, int H, long long R, const
     BinningView bv = binning_view((void*)binning_buf, R);
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
     const TilePlan plan = carve_plan(image_buf, s.geom.gx * s.geom.gy, bv);
-    R2X_TRY(launch_plan((cudaStream_t)stream, ranges, plan));
+    // the work plan of the forward is still valid: only the queue head and the arrival counters are rewound
+    R2X_CUDA_OK(cudaMemsetAsync(plan.counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    R2X_CUDA_OK(cudaMemsetAsync(plan.tile_done, 0, sizeof(uint32_t) * PLAN_DONE_SLOTS * (size_t)plan.num_tiles, (cudaStream_t)stream));
     return launch_raster_render((cudaStream_t)stream, W, H, s.geom, ranges, bv.point_list, plan, R, out_color);
 }
 
@@ -437,7 +439,8 @@ int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long
     BinningView bv = binning_view((void*)binning_buf, R);
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
     const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
-    R2X_TRY(launch_plan((cudaStream_t)stream, ranges, plan));
+    R2X_CUDA_OK(cudaMemsetAsync(plan.counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    R2X_CUDA_OK(cudaMemsetAsync(plan.tile_done, 0, sizeof(uint32_t) * PLAN_DONE_SLOTS * (size_t)plan.num_tiles, (cudaStream_t)stream));
     return launch_voxel_render((cudaStream_t)stream, vg, s.geom, ranges, bv.point_list, plan, R, out_volume);
 }
 
