@@ -1,6 +1,7 @@
 """Widening rows of SURVEY §8(f): fused losses, fused Adam, GaussianModel (accessors, densify / prune in one
 gather) -- each against a plain PyTorch statement of the reference's formula / sequence of operations."""
 import copy
+import os
 import math
 import types
 
