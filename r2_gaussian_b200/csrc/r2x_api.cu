@@ -464,7 +464,8 @@ int r2x_raster_backward(void* stream, int P, long long R, int W, int H, const fl
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
     const TilePlan plan = carve_plan(image_buf, s.geom.gx * s.geom.gy, bv);
-    if (R > 0) R2X_TRY(launch_raster_render_bwd(st, W, H, s.geom, ranges, bv.point_list, bv.inst_pos, plan, R, dL_dpix, inst_grad));
+    const uint32_t* inst_pos = direct_ok(s.geom.gx * s.geom.gy) ? nullptr : bv.inst_pos;   // direct binning: slots are derived
+    if (R > 0) R2X_TRY(launch_raster_render_bwd(st, W, H, s.geom, ranges, bv.point_list, inst_pos, plan, R, dL_dpix, inst_grad));
     R2X_TRY(debug_sync(st, debug, "raster render backward"));
     R2X_TRY(launch_raster_gauss_bwd(st, P, means3D, radii, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
                                     projmatrix, W, H, tan_fovx, tan_fovy, mode, s.geom, R, bv.inst_pos, inst_grad,
@@ -549,7 +550,8 @@ int r2x_voxel_backward(void* stream, int P, long long R, int nx, int ny, int nz,
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
     const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
-    if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, bv.inst_pos, plan, R, dL_dvol, inst_grad));
+    const uint32_t* inst_pos = direct_ok(vg.gx * vg.gy * vg.gz) ? nullptr : bv.inst_pos;
+    if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, inst_pos, plan, R, dL_dvol, inst_grad));
     R2X_TRY(debug_sync(st, debug, "voxel render backward"));
     R2X_TRY(launch_voxel_gauss_bwd(st, P, radii_x, radii_y, radii_z, scales, scale_modifier, rotations, cov3D_precomp, vg,
                                    s.geom, R, bv.inst_pos, inst_grad, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dscale,

@@ -648,7 +648,7 @@ int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, l
 //     range[t].x + prefix[b][t] + rank of the Gaussian among the CTA's Gaussians on tile t
 //                                 = wrank[w][t] + popc(mask[w][t] & lanes below)
 // => every tile list is ascending in Gaussian id (the stable order) without any search, sort or warp match, and the
-// instance's emission-order slot (backward moments) is a running counter.  Every CTA derives the tile ranges and its
+// instance's emission-order slot (backward moments) follows from offsets[] (emission_slot(), r2x_binning.cuh).  Every CTA derives the tile ranges and its
 // instance base itself (exclusive scans of tile_count / block_total: small and L2-hot), so nothing serial sits between
 // the column scan and this kernel; the publication of the ranges and of the work plan for the render is spread over
 // the CTAs.  Dynamic shared memory: mask[8][T] u32 | base[T] u32 | wrank[8][T] u8.
@@ -762,7 +762,6 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
         const uint32_t* plane = s_mask + (size_t)warp * T;
         const unsigned char* wr = s_wrank + (size_t)warp * T;
         const uint32_t below = (1u << lane) - 1u;
-        uint32_t slot = bbase + lex;
         for (uint32_t z = z0; z < z1; ++z)
             for (uint32_t y = y0; y < y1; ++y) {
                 const uint32_t rowb = (z * (uint32_t)gy + y) * (uint32_t)gx;
@@ -770,7 +769,6 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
                     const uint32_t t = rowb + x;
                     const uint32_t pos = s_base[t] + wr[t] + __popc(plane[t] & below);
                     point_list[pos] = (uint32_t)g;
-                    inst_pos[pos] = slot++;
                 }
             }
     }

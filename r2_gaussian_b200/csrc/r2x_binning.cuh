@@ -25,7 +25,7 @@ struct BinningView {
     uint32_t* vals[2];     // original instance index, ping-pong
     uint32_t* inst_g;      // [R] Gaussian id of instance i (emission order)
     uint32_t* point_list;  // [R] Gaussian id at sorted position s
-    uint32_t* inst_pos;    // [R] emission-order slot of the instance at tile-major position s (backward moments)
+    uint32_t* inst_pos;    // [R] emission-order slot of the instance at tile-major position s (backward moments; radix path only)
     uint32_t* hist;        // [256 * SORT_MAX_BLOCKS] digit-major per-block histograms
     uint2* extra_item;     // TilePlan::extra_item
     float* partial;        // TilePlan::partial
@@ -70,6 +70,20 @@ struct BinningView;
 TilePlan plan_view(void* image_buf_after_ranges, int num_tiles, const BinningView& bv);
 int launch_plan(cudaStream_t st, const uint2* ranges, const TilePlan& plan);
 int reset_plan_counter(cudaStream_t st, const TilePlan& plan, int which);
+
+// Emission-order slot of instance (Gaussian g, tile (tx,ty,tz)): the instances of a Gaussian are contiguous in emission
+// order, [offsets[g] - n_g, offsets[g]), tiles of its cube row-major (z, y, x).  Direct binning does not materialise
+// the per-instance slot array (it would cost one scattered 4-byte store per instance in the forward, which the
+// forward-only users never read); the backward derives the slot from three small per-Gaussian loads instead.
+__device__ __forceinline__ uint32_t emission_slot(const uint16_t* __restrict__ cube, const uint32_t* __restrict__ offsets,
+                                                  const uint32_t* __restrict__ tiles_touched, uint32_t g, uint32_t tx,
+                                                  uint32_t ty, uint32_t tz) {
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(cube + 6 * (size_t)g);
+    const uint32_t c01 = c[0], c23 = c[1], c45 = c[2];
+    const uint32_t x0 = c01 & 0xffff, y0 = c01 >> 16, z0 = c23 & 0xffff, x1 = c23 >> 16, y1 = c45 & 0xffff;
+    const uint32_t w = x1 - x0, h = y1 - y0;
+    return offsets[g] - tiles_touched[g] + ((tz - z0) * h + (ty - y0)) * w + (tx - x0);
+}
 
 // chunk `chunk` of `nch` equal slices of the tile list [r.x, r.y)
 __device__ __forceinline__ void plan_slice(const uint2 r, int chunk, int nch, uint32_t& begin, int& n) {

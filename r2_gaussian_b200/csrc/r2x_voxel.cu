@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list,
-                                                               const uint32_t* __restrict__ inst_pos,
+                                                               const uint32_t* __restrict__ inst_pos, VoxelGeom geom,
                                                                const float4* __restrict__ rec, TilePlan pl,
                                                                const float* __restrict__ dL_dvol,
                                                                float4* __restrict__ inst_grad) {
@@ -487,7 +487,9 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
             Sxy = fmaf(dx, Xy, Sxy);
             Sxz = fmaf(dx, Xz, Sxz);
         }
-        const uint32_t slot = inst_pos[s];   // emission-order index: a Gaussian's instances are contiguous there
+        // emission-order index: a Gaussian's instances are contiguous there
+        const uint32_t slot = inst_pos ? inst_pos[s]
+                                       : emission_slot(geom.cube, geom.offsets, geom.tiles_touched, g, (uint32_t)tx, (uint32_t)ty, (uint32_t)tz);
         inst_grad[3 * (size_t)slot] = make_float4(S0, Sx, Sy, Sz);
         inst_grad[3 * (size_t)slot + 1] = make_float4(Sxx, Sxy, Sxz, Syy);
         inst_grad[3 * (size_t)slot + 2] = make_float4(Syz, Szz, 0.f, 0.f);
@@ -627,7 +629,7 @@ int launch_voxel_render_bwd(cudaStream_t st, const VoxelGrid& vg, const VoxelGeo
                             long long R_launch, const float* dL_dvol, float4* inst_grad) {
     const long long items = (long long)plan.num_tiles + R_launch / PLAN_CHUNK + 1;
     R2X_CUDA_OK(cudaMemsetAsync(plan.counter + 1, 0, sizeof(uint32_t), st));
-    voxel_render_bwd_kernel<<<vpersistent_grid(items), 256, 0, st>>>(vg, ranges, point_list, inst_pos, geom.rec, plan,
+    voxel_render_bwd_kernel<<<vpersistent_grid(items), 256, 0, st>>>(vg, ranges, point_list, inst_pos, geom, geom.rec, plan,
                                                                      dL_dvol, inst_grad);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -33,7 +33,10 @@ def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, ma
 
 def build_rotation(q):
     """[N,4] quaternions (r,x,y,z), normalised here -> [N,3,3] rotation matrices."""
-    q = q / q.norm(dim=1, keepdim=True)
+    # the norm is spelt out term by term (not q.norm()): the split children's positions depend on these bits, and the
+    # reference sums r^2 + x^2 + y^2 + z^2 left to right (utils/gaussian_utils.py:50-54)
+    norm = torch.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    q = q / norm[:, None]
     r, x, y, z = q.unbind(1)
     rows = (1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
             2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),

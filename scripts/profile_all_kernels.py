@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""One pass through every hand-written kernel of the forward / backward / voxel / training chains, for
+    ncu --set full --profile-from-start off -f -o gpurun_out/r02_all_kernels python scripts/profile_all_kernels.py
+(the profiled region is bracketed with cudaProfilerStart/Stop after one warm-up pass).  `--summarize <rep>` turns the
+report into profiles/-ready CSV rows: duration, DRAM bytes and GB/s, issue-slot utilisation, dominant pipe."""
+import csv
+import os
+import subprocess
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def workload():
+    import numpy as np
+    import torch
+
+    from r2_gaussian_b200 import _C, compact, losses, scene
+    from r2_gaussian_b200.gaussian_model import GaussianModel
+    from r2_gaussian_b200.simple_knn import distCUDA2
+
+    dev = torch.device("cuda")
+    E = torch.Tensor([])
+    cloud = scene.make_cloud(100_000, kind="init", seed=0)
+    big = scene.make_cloud(500_000, kind="init", seed=0)
+    view = scene.make_view(scene.cone_beam_scanner(512, 256), 0.0)
+    t = lambda a: torch.tensor(a, device=dev)
+    m, s, r, d = t(cloud.means), t(cloud.scales), t(cloud.rotations), t(cloud.density)
+    bm, bs, br, bd = t(big.means), t(big.scales), t(big.rotations), t(big.density)
+    vm, pm, cp = t(view.viewmatrix), t(view.projmatrix), t(view.campos)
+    dL = torch.randn(1, 512, 512, device=dev)
+    dV = torch.randn(32, 32, 32, device=dev)
+    gt = torch.rand(1, 512, 512, device=dev)
+    opt_args = types.SimpleNamespace(
+        position_lr_init=2e-4, position_lr_final=2e-5, position_lr_max_steps=30000,
+        density_lr_init=1e-2, density_lr_final=1e-3, density_lr_max_steps=30000,
+        scaling_lr_init=5e-3, scaling_lr_final=5e-4, scaling_lr_max_steps=30000,
+        rotation_lr_init=1e-3, rotation_lr_final=1e-4, rotation_lr_max_steps=30000)
+    import contextlib
+    import io
+    gm = GaussianModel((0.001, 1.0))
+    with contextlib.redirect_stdout(io.StringIO()):
+        gm.create_from_pcd(cloud.means[:20000], np.maximum(cloud.density[:20000], 1e-3), 1.0)
+    gm.training_setup(opt_args)
+
+    def once():
+        R, img, radii, geom, binning, imgb = _C.rasterize_gaussians(m, d, s, r, 1.0, E, vm, pm, view.tanfovx, view.tanfovy,
+                                                                     512, 512, cp, False, view.mode, False)
+        _C.rasterize_gaussians_backward(m, radii, s, r, 1.0, E, vm, pm, view.tanfovx, view.tanfovy, dL, cp, geom, R,
+                                        binning, imgb, view.mode, False)
+        _C.voxelize_gaussians(bm, bd, bs, br, 1.0, E, 256, 256, 256, 2.0, 2.0, 2.0, 0.0, 0.0, 0.0, False, False)
+        R2, vol, rx, ry, rz, g2, b2, i2 = _C.voxelize_gaussians(m, d, s, r, 1.0, E, 32, 32, 32, 0.25, 0.25, 0.25, 0.3, -0.4,
+                                                                 0.1, False, False)
+        _C.voxelize_gaussians_backward(m, rx, ry, rz, s, r, 1.0, E, dV, g2, R2, b2, i2, 32, 32, 32, 0.25, 0.25, 0.25, 0.3,
+                                       -0.4, 0.1, False)
+        # radix-path backward (volume with more than 4096 tiles)
+        R3, vol3, ax, ay, az, g3, b3, i3 = _C.voxelize_gaussians(m, d, s, r, 1.0, E, 144, 144, 144, 2.0, 2.0, 2.0, 0.0, 0.0,
+                                                                  0.0, False, False)
+        _C.voxelize_gaussians_backward(m, ax, ay, az, s, r, 1.0, E, torch.randn_like(vol3), g3, R3, b3, i3, 144, 144, 144,
+                                       2.0, 2.0, 2.0, 0.0, 0.0, 0.0, False)
+        a = img.detach().clone().requires_grad_(True)
+        losses.image_loss(a, gt, 0.25)["total"].backward()
+        v = vol.detach().clone().requires_grad_(True)
+        losses.tv_3d_loss(v, "mean").backward()
+        for _, attr in (("xyz", "_xyz"), ("density", "_density"), ("scaling", "_scaling"), ("rotation", "_rotation")):
+            p = getattr(gm, attr)
+            p.grad = torch.randn_like(p) * 1e-3
+        gm.optimizer.step()
+        distCUDA2(m)
+        mask = torch.rand(100_000, device=dev) < 0.5
+        idx, cnt = compact.select_rows(mask)
+        k = compact.read_counts(cnt)[0]
+        compact.gather_rows([(m, None), (s, None), (r, None), (d, None)], idx, k)
+        torch.cuda.synchronize()
+
+    once()
+    torch.cuda.profiler.start()
+    once()
+    torch.cuda.profiler.stop()
+
+
+KEYS = {
+    "gpu__time_duration.sum": "duration_us",
+    "dram__bytes_read.sum": "dram_read_MB",
+    "dram__bytes_write.sum": "dram_write_MB",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "pipe_xu_pct",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "pipe_fma_pct",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active": "pipe_alu_pct",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "pipe_lsu_pct",
+    "launch__registers_per_thread": "registers",
+    "launch__grid_size": "grid",
+    "launch__block_size": "block",
+    "smsp__inst_executed.sum": "warp_instructions",
+}
+
+
+def summarize(rep, out_csv):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    kn = col["Kernel Name"]
+    out = [["kernel"] + list(KEYS.values()) + ["dram_GBps", "dominant_pipe"]]
+    for r in rows[2:]:
+        if len(r) <= kn:
+            continue
+        name = r[kn].split("(")[0].replace("void ", "")
+        vals = {}
+        for k, short in KEYS.items():
+            if k in col:
+                try:
+                    v = float(r[col[k]].replace(",", ""))
+                except ValueError:
+                    v = float("nan")
+                u = units[col[k]]
+                if short == "duration_us":
+                    v = v / 1000.0 if u in ("nsecond", "ns") else (v * 1000.0 if u in ("msecond", "ms") else v)
+                if short.endswith("_MB"):
+                    v = v / 1e6 if u == "byte" else (v / 1e3 if u == "Kbyte" else (v * 1e3 if u == "Gbyte" else v))
+                vals[short] = v
+        dur = vals.get("duration_us", float("nan"))
+        gbps = (vals.get("dram_read_MB", 0) + vals.get("dram_write_MB", 0)) / dur * 1e-3 * 1e6 / 1e3 if dur == dur and dur > 0 else float("nan")
+        pipes = {p: vals.get(p, 0) for p in ("pipe_xu_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_lsu_pct")}
+        dom = max(pipes, key=pipes.get) if pipes else ""
+        out.append([name] + [f"{vals.get(s, float('nan')):.4g}" for s in KEYS.values()] + [f"{gbps:.4g}", dom])
+    with open(out_csv, "w", newline="") as f:
+        csv.writer(f).writerows(out)
+    print(f"wrote {out_csv}: {len(out) - 1} kernel launches")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--summarize":
+        summarize(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "r02_ncu_all_kernels.csv"))
+    else:
+        workload()
