@@ -1,6 +1,7 @@
 // r2x_common.cuh -- shared device helpers for the sm_100a X-ray Gaussian kernels.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "r2x_matcalc.cuh"
 
@@ -159,7 +160,12 @@ inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static int enabled = -1;          // R2X_NO_PDL=1: plain stream-ordered launches (measurement of what PDL buys)
+    if (enabled < 0) {
+        const char* e = getenv("R2X_NO_PDL");
+        enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    cfg.numAttrs = enabled ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
