@@ -38,16 +38,15 @@ constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096
 constexpr int SORT_MAX_BLOCKS = 296;                   // 2 CTAs per SM on 148 SMs
 
 // ---- work plan for the per-tile kernels -------------------------------------------------------
-// Per-tile lists are cut into chunks of at most C instances (C = the launch's chunk size, 64..PLAN_CHUNK, chosen ON
-// THE DEVICE from the instance count R so that the item count stays a few times the number of resident CTAs:
-// plan_chunk_for); a tile of n instances gets ceil(n / C) chunks of EQUAL length (+-1).  A (tile, chunk) pair is one
+// Per-tile lists are cut into chunks of at most C instances (C = the launch's chunk size, 64..PLAN_CHUNK, decided ON
+// THE DEVICE by plan_chunk_for: PLAN_CHUNK unless overridden); a tile of n instances gets ceil(n / C) chunks of EQUAL
+// length (+-1).  A (tile, chunk) pair is one
 // work item of the render kernels, handed out through an atomic counter, so that SM load is balanced no matter how
 // uneven the per-tile counts are.  Items [0,T) are chunk 0 of every tile (also of empty tiles: they write the
 // zeros); items [T, T+E) are the extra chunks, looked up in `extra_item`.  A tile with several chunks combines its
 // partial sums in chunk order (the last-arriving CTA does it) => deterministic.
 constexpr int PLAN_CHUNK = 256;       // largest chunk = records staged per work item
 constexpr int PLAN_MIN_CHUNK = 64;    // smallest chunk (sizes extra_item / partial)
-constexpr int PLAN_TARGET_ITEMS = 148 * 6 * 4;   // aim: ~4 items per resident CTA of the raster render kernel
 constexpr int PLAN_DONE_SLOTS = 8;   // arrival counters per tile (one per warp of the raster render CTA)
 struct TilePlan {
     uint32_t* extra_off;  // [T+1] exclusive scan of (chunks_t - 1); [T] = E
@@ -61,8 +60,12 @@ struct TilePlan {
 };
 __host__ __device__ __forceinline__ uint32_t plan_chunk_for(uint32_t R, int chunk_override) {
     if (chunk_override > 0) return (uint32_t)(chunk_override < PLAN_MIN_CHUNK ? PLAN_MIN_CHUNK : (chunk_override > PLAN_CHUNK ? PLAN_CHUNK : chunk_override));
-    uint32_t c = (R / PLAN_TARGET_ITEMS + 31u) & ~31u;
-    return c < (uint32_t)PLAN_MIN_CHUNK ? (uint32_t)PLAN_MIN_CHUNK : (c > (uint32_t)PLAN_CHUNK ? (uint32_t)PLAN_CHUNK : c);
+    // Measured (B200, warp-specialised render kernel): the largest chunk wins at every instance count -- 256 vs 192 / 128 /
+    // 64 on the 1.06 M-instance headline scene: 78 / 84 / 97 / 132 us -- because a work item costs the producer warp a
+    // fixed latency chain; small shards (one chunk per tile) are bound by that chain, not by the math.  The device-side
+    // choice is kept as a mechanism (R2X_CHUNK for experiments).
+    (void)R;
+    return (uint32_t)PLAN_CHUNK;
 }
 int plan_chunk_override();   // R2X_CHUNK from the environment (0 when unset)
 size_t plan_bytes(int num_tiles);
