@@ -189,6 +189,41 @@ typedef struct r2x_adam_group {
 int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
                   long long step);
 
+/* ---- folded parameter activations ------------------------------------------ */
+/* The reference applies softplus (density), a bounded sigmoid or exp (scale) and normalize (rotation) as separate torch
+ * kernels before every render() / query() and differentiates through them with autograd
+ * (r2_gaussian/gaussian/gaussian_model.py:37-64, :112-126).  The *_raw entry points take the RAW parameters, apply the
+ * activations inside the preprocess kernels and return the gradients with respect to the raw parameters (the other
+ * arguments and buffers are those of the plain calls; cov3D_precomp does not apply).
+ *   scale_mode 0: scale = exp(raw);  1: scale = scale_lo + (scale_hi - scale_lo) * sigmoid(raw). */
+typedef struct r2x_activation {
+    int scale_mode;
+    float scale_lo, scale_hi;
+} r2x_activation;
+int r2x_raster_forward_async_raw(void* stream, int P, int W, int H, const float* means3D, const float* raw_density,
+                                 const float* raw_scales, float scale_modifier, const float* raw_rotations,
+                                 const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                                 float tan_fovy, int mode, float* out_color, int* radii, void* geom_buf, void* image_buf,
+                                 void* binning_buf, long long capacity, uint32_t* status_dev, const r2x_activation* act);
+int r2x_raster_backward_raw(void* stream, int P, long long R, int W, int H, const float* means3D, const float* raw_scales,
+                            float scale_modifier, const float* raw_rotations, const float* viewmatrix,
+                            const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                            const void* geom_buf, const void* binning_buf, const void* image_buf, void* scratch,
+                            const float* dL_dpix, float* dL_dmean2D, float* dL_draw_density, float* dL_dmean3D,
+                            float* dL_dcov3D, float* dL_draw_scale, float* dL_draw_rot, int mode, const r2x_activation* act);
+int r2x_voxel_forward_async_raw(void* stream, int P, int nx, int ny, int nz, float sx, float sy, float sz, float cx,
+                                float cy, float cz, const float* means3D, const float* raw_density,
+                                const float* raw_scales, float scale_modifier, const float* raw_rotations,
+                                float* out_volume, int* radii_x, int* radii_y, int* radii_z, void* geom_buf,
+                                void* image_buf, void* binning_buf, long long capacity, uint32_t* status_dev,
+                                const r2x_activation* act);
+int r2x_voxel_backward_raw(void* stream, int P, long long R, int nx, int ny, int nz, float sx, float sy, float sz, float cx,
+                           float cy, float cz, const float* means3D, const float* raw_scales, float scale_modifier,
+                           const float* raw_rotations, const int* radii_x, const int* radii_y, const int* radii_z,
+                           const void* geom_buf, const void* binning_buf, const void* image_buf, void* scratch,
+                           const float* dL_dvol, float* dL_draw_density, float* dL_dmean3D, float* dL_dcov3D,
+                           float* dL_draw_scale, float* dL_draw_rot, const r2x_activation* act);
+
 /* ---- device-side row compaction for densify / clone / split / prune ------------------------------ */
 /* Replaces the boolean-mask indexing + torch.cat sequence of the reference's optimizer surgery
  * (r2_gaussian/gaussian/gaussian_model.py:335-403, :503-550).  r2x_mask_select turns a byte mask into the stable

@@ -52,6 +52,14 @@ PROTOTYPES = {
     "r2x_tv3d_scratch_bytes": (_sz, [_i, _i, _i]),
     "r2x_tv3d_loss": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz]),
     "r2x_adam_step": (_i, [_vp, _i, _vp, C.c_double, C.c_double, C.c_double, _ll]),
+    "r2x_raster_forward_async_raw": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp,
+                                          _vp, _ll, _vp, _vp]),
+    "r2x_raster_backward_raw": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "r2x_voxel_forward_async_raw": (_i, [_vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, _ll, _vp, _vp]),
+    "r2x_voxel_backward_raw": (_i, [_vp, _i, _ll, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "r2x_mask_select_scratch_bytes": (_sz, [_i]),
     "r2x_mask_select": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz]),
     "r2x_gather_rows": (_i, [_vp, _i, _vp, _vp, _ll]),
@@ -63,6 +71,11 @@ PROTOTYPES = {
     "r2x_peer_allreduce_sum": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp]),
     "r2x_peer_allreduce_sum_t": (_i, [_vp, _i, _i, _vp, _vp, C.c_uint32, _vp, _ll, _vp, _ll]),
 }
+
+
+class ActivationDesc(C.Structure):
+    """Mirror of `r2x_activation` (include/r2x.h)."""
+    _fields_ = [("scale_mode", C.c_int), ("scale_lo", C.c_float), ("scale_hi", C.c_float)]
 
 
 class GatherDesc(C.Structure):

@@ -14,6 +14,9 @@ int launch_adam(cudaStream_t st, int ngroups, const r2x_adam_group* groups, doub
                 long long step);
 
 static thread_local std::string g_err;
+static thread_local Activation g_act = {0, 0, 0.f, 0.f};
+Activation current_activation() { return g_act; }
+void set_activation(const Activation* a) { g_act = a ? *a : Activation{0, 0, 0.f, 0.f}; }
 
 int fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
@@ -583,6 +586,69 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     }
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// ---- folded activations: the same four calls on RAW density / scale / rotation parameters -----------------------
+namespace {
+struct ActScope {
+    explicit ActScope(const r2x_activation* a) {
+        Activation v = {1, a ? a->scale_mode : 0, a ? a->scale_lo : 0.f, a ? a->scale_hi : 0.f};
+        set_activation(&v);
+    }
+    ~ActScope() { set_activation(nullptr); }
+};
+}  // namespace
+
+int r2x_raster_forward_async_raw(void* stream, int P, int W, int H, const float* means3D, const float* raw_density,
+                                 const float* raw_scales, float scale_modifier, const float* raw_rotations,
+                                 const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                                 float tan_fovy, int mode, float* out_color, int* radii, void* geom_buf, void* image_buf,
+                                 void* binning_buf, long long capacity, uint32_t* status_dev, const r2x_activation* act) {
+    if (!act || !raw_scales || !raw_rotations) return fail_msg(R2X_ERR_INVALID, "r2x_raster_forward_async_raw: null argument");
+    ActScope scope(act);
+    return r2x_raster_forward_async(stream, P, W, H, means3D, raw_density, raw_scales, scale_modifier, raw_rotations, nullptr,
+                                    viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, 0, mode, out_color, radii, geom_buf,
+                                    image_buf, binning_buf, capacity, status_dev);
+}
+
+int r2x_raster_backward_raw(void* stream, int P, long long R, int W, int H, const float* means3D, const float* raw_scales,
+                            float scale_modifier, const float* raw_rotations, const float* viewmatrix,
+                            const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                            const void* geom_buf, const void* binning_buf, const void* image_buf, void* scratch,
+                            const float* dL_dpix, float* dL_dmean2D, float* dL_draw_density, float* dL_dmean3D,
+                            float* dL_dcov3D, float* dL_draw_scale, float* dL_draw_rot, int mode, const r2x_activation* act) {
+    if (!act || !raw_scales || !raw_rotations) return fail_msg(R2X_ERR_INVALID, "r2x_raster_backward_raw: null argument");
+    ActScope scope(act);
+    return r2x_raster_backward(stream, P, R, W, H, means3D, raw_scales, scale_modifier, raw_rotations, nullptr, viewmatrix,
+                               projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buf, binning_buf, image_buf, scratch,
+                               dL_dpix, dL_dmean2D, dL_draw_density, nullptr, dL_dmean3D, dL_dcov3D, dL_draw_scale,
+                               dL_draw_rot, mode, 0);
+}
+
+int r2x_voxel_forward_async_raw(void* stream, int P, int nx, int ny, int nz, float sx, float sy, float sz, float cx,
+                                float cy, float cz, const float* means3D, const float* raw_density,
+                                const float* raw_scales, float scale_modifier, const float* raw_rotations,
+                                float* out_volume, int* radii_x, int* radii_y, int* radii_z, void* geom_buf,
+                                void* image_buf, void* binning_buf, long long capacity, uint32_t* status_dev,
+                                const r2x_activation* act) {
+    if (!act || !raw_scales || !raw_rotations) return fail_msg(R2X_ERR_INVALID, "r2x_voxel_forward_async_raw: null argument");
+    ActScope scope(act);
+    return r2x_voxel_forward_async(stream, P, nx, ny, nz, sx, sy, sz, cx, cy, cz, means3D, raw_density, raw_scales,
+                                   scale_modifier, raw_rotations, nullptr, 0, out_volume, radii_x, radii_y, radii_z, geom_buf,
+                                   image_buf, binning_buf, capacity, status_dev);
+}
+
+int r2x_voxel_backward_raw(void* stream, int P, long long R, int nx, int ny, int nz, float sx, float sy, float sz, float cx,
+                           float cy, float cz, const float* means3D, const float* raw_scales, float scale_modifier,
+                           const float* raw_rotations, const int* radii_x, const int* radii_y, const int* radii_z,
+                           const void* geom_buf, const void* binning_buf, const void* image_buf, void* scratch,
+                           const float* dL_dvol, float* dL_draw_density, float* dL_dmean3D, float* dL_dcov3D,
+                           float* dL_draw_scale, float* dL_draw_rot, const r2x_activation* act) {
+    if (!act || !raw_scales || !raw_rotations) return fail_msg(R2X_ERR_INVALID, "r2x_voxel_backward_raw: null argument");
+    ActScope scope(act);
+    return r2x_voxel_backward(stream, P, R, nx, ny, nz, sx, sy, sz, cx, cy, cz, means3D, raw_scales, scale_modifier,
+                              raw_rotations, nullptr, radii_x, radii_y, radii_z, geom_buf, binning_buf, image_buf, scratch,
+                              dL_dvol, dL_draw_density, dL_dmean3D, dL_dcov3D, dL_draw_scale, dL_draw_rot, 0);
 }
 
 size_t r2x_knn_scratch_bytes(int P) { return r2x::knn_scratch_bytes(P); }

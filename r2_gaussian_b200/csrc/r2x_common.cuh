@@ -20,6 +20,45 @@ int fail(cudaError_t e, const char* what, const char* file, int line);
 int fail_msg(int code, const char* msg);
 
 // ---------------------------------------------------------------------------------------------
+// Folded parameter activations (the reference applies them as separate torch kernels,
+// gaussian_model.py:112-126): with `enabled` the preprocess kernels read the RAW parameters and apply
+//     density = softplus(raw)              (torch.nn.Softplus: x > 20 ? x : log1p(exp(x)))
+//     scale   = lo + (hi - lo) sigmoid(raw)   [scale_mode 1]   or   exp(raw)   [scale_mode 0]
+//     rotation = raw / max(|raw|, 1e-12)   (torch.nn.functional.normalize)
+// themselves, and the per-Gaussian backward kernels return the gradients with respect to the raw parameters.
+// ---------------------------------------------------------------------------------------------
+struct Activation {
+    int enabled;
+    int scale_mode;
+    float lo, hi;
+};
+Activation current_activation();                 // set by the *_raw entry points for the duration of one call (r2x_api.cu)
+void set_activation(const Activation* a);
+
+__device__ __forceinline__ float act_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float act_scale(const Activation& a, float x) {
+    return a.scale_mode ? __fadd_rn(__fmul_rn(act_sigmoid(x), a.hi - a.lo), a.lo) : expf(x);
+}
+__device__ __forceinline__ float act_scale_grad(const Activation& a, float x) {   // d scale / d raw
+    if (!a.scale_mode) return expf(x);
+    const float sg = act_sigmoid(x);
+    return (a.hi - a.lo) * sg * (1.0f - sg);
+}
+__device__ __forceinline__ float4 act_normalize(float4 q, float& norm) {
+    norm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    const float inv = 1.0f / norm;
+    return make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+// gradient of q_hat = q / |q| pulled back to q:  (dq_hat - q_hat (q_hat . dq_hat)) / |q|
+__device__ __forceinline__ void act_normalize_grad(float4 qn, float norm, float* dr) {
+    const float dot = qn.x * dr[0] + qn.y * dr[1] + qn.z * dr[2] + qn.w * dr[3];
+    const float inv = 1.0f / norm;
+    dr[0] = (dr[0] - qn.x * dot) * inv; dr[1] = (dr[1] - qn.y * dot) * inv;
+    dr[2] = (dr[2] - qn.z * dot) * inv; dr[3] = (dr[3] - qn.w * dot) * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Exactly-rounded float32 building blocks.  The reference's radii / tile rectangles / depth bits
 // must be reproduced bit for bit, so every operation on that path is written with an explicit
 // rounding intrinsic: the compiler can neither fuse nor re-associate them.  The sequence mirrors

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
     int P, const float* __restrict__ means, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ cov3D_precomp,
     VoxelGrid vg, int use_tma, int* __restrict__ radii_x, int* __restrict__ radii_y, int* __restrict__ radii_z,
-    VoxelGeom geom, DirectBin db, int direct) {
+    VoxelGeom geom, DirectBin db, int direct, Activation act) {
     extern __shared__ __align__(16) uint32_t s_hist[];   // [T] when direct binning
     __shared__ __align__(16) float s_means[VPRE_THREADS * 3];
     __shared__ __align__(16) float s_scales[VPRE_THREADS * 3];
@@ -103,6 +103,12 @@ __global__ void __launch_bounds__(VPRE_THREADS) voxel_preprocess_kernel(
         s0 = scales[3 * (size_t)g]; s1 = scales[3 * (size_t)g + 1]; s2 = scales[3 * (size_t)g + 2];
         q = rots ? make_float4(rots[4 * (size_t)g], rots[4 * (size_t)g + 1], rots[4 * (size_t)g + 2], rots[4 * (size_t)g + 3])
                  : make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    if (act.enabled && live) {      // raw parameters: apply the activations here
+        rho = act_softplus(rho);
+        s0 = act_scale(act, s0); s1 = act_scale(act, s1); s2 = act_scale(act, s2);
+        float nrm;
+        q = act_normalize(q, nrm);
     }
     int rxi = 0, ryi = 0, rzi = 0;
     uint32_t ntiles = 0, c01 = 0, c23 = 0, c45 = 0;
@@ -505,7 +511,7 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
     const float* __restrict__ cov3D_precomp, VoxelGrid vg, VoxelGeom geom, long long capacity,
     const uint32_t* __restrict__ inst_pos,
     const float4* __restrict__ inst_grad, float* __restrict__ dL_dopacity, float* __restrict__ dL_dmean3D,
-    float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+    float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscale, float* __restrict__ dL_drot, Activation act) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= P) return;
     const bool live = (radii_x[g] > 0) && (radii_y[g] > 0) && (radii_z[g] > 0);
@@ -530,9 +536,15 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
         float c3[6];
+        float raw_s[3] = {0.f, 0.f, 0.f}, qnorm = 1.f;
         if (have_sr) {
             s0 = scales[3 * (size_t)g]; s1 = scales[3 * (size_t)g + 1]; s2 = scales[3 * (size_t)g + 2];
             q = make_float4(rots[4 * (size_t)g], rots[4 * (size_t)g + 1], rots[4 * (size_t)g + 2], rots[4 * (size_t)g + 3]);
+            if (act.enabled) {
+                raw_s[0] = s0; raw_s[1] = s1; raw_s[2] = s2;
+                s0 = act_scale(act, s0); s1 = act_scale(act, s1); s2 = act_scale(act, s2);
+                q = act_normalize(q, qnorm);
+            }
             cov3d_from_scale_rot(s0, s1, s2, scale_modifier, q, c3);
         } else {
 #pragma unroll
@@ -542,7 +554,7 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
         float inv[6];
         voxel_inverse(vc, inv);
         // VOX/backward.cu:348-370 with the per-pair sums factored into moments
-        dop = S0;
+        dop = act.enabled ? S0 * (1.0f - expf(-rho)) : S0;     // raw density: softplus' = 1 - exp(-rho)
         dmean[0] = rho * (-inv[0] * Sx - inv[1] * Sy - inv[2] * Sz) * vg.dvx;   // note: x dVoxel, as the reference
         dmean[1] = rho * (-inv[3] * Sy - inv[1] * Sx - inv[4] * Sz) * vg.dvy;
         dmean[2] = rho * (-inv[5] * Sz - inv[2] * Sx - inv[4] * Sy) * vg.dvz;
@@ -564,7 +576,14 @@ __global__ void __launch_bounds__(256) voxel_gauss_bwd_kernel(
             const float Mm[9] = {vg.ix, 0.f, 0.f, 0.f, vg.iy, 0.f, 0.f, 0.f, vg.iz};
             dcov3d_from_dhat(Mm, dh, dcov);
         }
-        if (have_sr) cov3d_backward(s0, s1, s2, scale_modifier, q, dcov, ds, dr);
+        if (have_sr) {
+            cov3d_backward(s0, s1, s2, scale_modifier, q, dcov, ds, dr);
+            if (act.enabled) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ds[k] *= act_scale_grad(act, raw_s[k]);
+                act_normalize_grad(q, qnorm, dr);
+            }
+        }
     }
     dL_dopacity[g] = dop;
 #pragma unroll
@@ -605,7 +624,7 @@ int launch_voxel_preprocess(cudaStream_t st, int P, const float* means, const fl
     const size_t smem = db ? (size_t)db->num_tiles * sizeof(uint32_t) : 0;
     voxel_preprocess_kernel<<<(P + VPRE_THREADS - 1) / VPRE_THREADS, VPRE_THREADS, smem, st>>>(
         P, means, scales, scale_modifier, rots, opac, cov3D_precomp, vg, use_tma, radii_x, radii_y, radii_z, geom, dbv,
-        db ? 1 : 0);
+        db ? 1 : 0, current_activation());
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -643,7 +662,7 @@ int launch_voxel_gauss_bwd(cudaStream_t st, int P, const int* radii_x, const int
     if (P <= 0) return 0;
     voxel_gauss_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii_x, radii_y, radii_z, scales, scale_modifier, rots,
                                                              cov3D_precomp, vg, geom, capacity, inst_pos, inst_grad, dL_dopacity,
-                                                             dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot);
+                                                             dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot, current_activation());
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -85,6 +85,12 @@ class GaussianModel:
     def get_density(self):
         return self.density_activation(self._density)
 
+    def raw_parameters(self):
+        """Raw (pre-activation) parameters + what the kernels need to apply the activations themselves
+        (`fused.py`: softplus, bounded sigmoid or exp, normalize folded into preprocess / per-Gaussian backward)."""
+        return {"density": self._density, "scaling": self._scaling, "rotation": self._rotation,
+                "scale_bound": None if self.scale_bound is None else (float(self.scale_bound[0]), float(self.scale_bound[1]))}
+
     def get_covariance(self, scaling_modifier=1):
         return self.covariance_activation(self.get_scaling, scaling_modifier, self._rotation)
 

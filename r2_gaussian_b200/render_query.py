@@ -14,9 +14,19 @@ import math
 
 import torch
 
+from . import fused
 from .rasterization import GaussianRasterizationSettings, GaussianRasterizer
 from .sharded import sharded_sum
 from .voxelization import GaussianVoxelizationSettings, GaussianVoxelizer
+
+
+def _raw_parameters(pc, pipe):
+    """The model's raw parameters when the activations can be folded into the kernels (fused.py): this repository's
+    GaussianModel, covariance not precomputed in Python, debug off."""
+    if not fused.enabled() or getattr(pipe, "compute_cov3D_python", False) or getattr(pipe, "debug", False):
+        return None
+    get = getattr(pc, "raw_parameters", None)
+    return get() if callable(get) else None
 
 
 def _covariance_inputs(pc, pipe, scaling_modifier):
@@ -33,6 +43,10 @@ def query(pc, center, nVoxel, sVoxel, pipe, scaling_modifier=1.0):
         sVoxel_x=float(sVoxel[0]), sVoxel_y=float(sVoxel[1]), sVoxel_z=float(sVoxel[2]),
         center_x=float(center[0]), center_y=float(center[1]), center_z=float(center[2]),
         prefiltered=False, debug=bool(getattr(pipe, "debug", False)))
+    raw = _raw_parameters(pc, pipe)
+    if raw is not None:
+        vol, radii = fused.voxelize_raw(pc.get_xyz, raw, settings)
+        return {"vol": sharded_sum(vol), "radii": radii}
     scales, rotations, cov3D = _covariance_inputs(pc, pipe, scaling_modifier)
     vol, radii = GaussianVoxelizer(voxel_settings=settings)(
         means3D=pc.get_xyz, opacities=pc.get_density, scales=scales, rotations=rotations, cov3D_precomp=cov3D)
@@ -63,6 +77,11 @@ def render(viewpoint_camera, pc, pipe, scaling_modifier=1.0):
         viewmatrix=viewpoint_camera.world_view_transform, projmatrix=viewpoint_camera.full_proj_transform,
         campos=viewpoint_camera.camera_center, prefiltered=False, mode=mode,
         debug=bool(getattr(pipe, "debug", False)))
+    raw = _raw_parameters(pc, pipe)
+    if raw is not None:
+        image, radii = fused.rasterize_raw(xyz, screenspace_points, raw, settings)
+        return {"render": sharded_sum(image), "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0, "radii": radii}
     scales, rotations, cov3D = _covariance_inputs(pc, pipe, scaling_modifier)
     image, radii = GaussianRasterizer(raster_settings=settings)(
         means3D=xyz, means2D=screenspace_points, opacities=pc.get_density, scales=scales, rotations=rotations,

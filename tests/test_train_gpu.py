@@ -491,3 +491,40 @@ def test_select_and_gather_rows_against_torch_indexing():
         assert torch.equal(out[0], torch.cat((a, extra))[sel.long()])
         assert torch.equal(out[1], torch.cat((b, torch.zeros(7, device="cuda")))[sel.long()])
         assert torch.equal(out[2], torch.cat((a, torch.zeros(7, 3, device="cuda")))[sel.long()])
+
+
+@pytest.mark.parametrize("bounded", [True, False])
+def test_folded_activations_match_the_torch_activations(bounded, monkeypatch):
+    """render() / query() on raw parameters (activations inside the preprocess kernels, gradients w.r.t. the raw
+    parameters from the per-Gaussian backward kernels) against the plain path (torch softplus / sigmoid / normalize +
+    autograd), image, volume and every parameter gradient."""
+    from r2_gaussian_b200 import scene
+    from r2_gaussian_b200.render_query import query, render
+    pipe = types.SimpleNamespace(compute_cov3D_python=False, debug=False)
+    cam = scene.camera_from_view(scene.make_view(scene.cone_beam_scanner(128, 64), 0.6))
+    rng = np.random.default_rng(3)
+    groups = ("_xyz", "_density", "_scaling", "_rotation")
+
+    def run(fused_on):
+        monkeypatch.setenv("R2X_FUSED_ACTIVATIONS", "1" if fused_on else "0")
+        gm, _, _ = _make_model(n=3000, seed=7, scale_bound=(0.0005, 0.5) if bounded else None)
+        with torch.no_grad():
+            gm._rotation += torch.tensor(rng.normal(scale=0.3, size=(3000, 4)).astype(np.float32), device="cuda")
+            gm._scaling += torch.tensor(rng.normal(scale=0.2, size=(3000, 3)).astype(np.float32), device="cuda")
+        pkg = render(cam, gm, pipe)
+        vol = query(gm, [0.1, 0.0, -0.1], [32, 32, 32], [0.5, 0.5, 0.5], pipe)["vol"]
+        g = torch.Generator("cuda").manual_seed(5)
+        loss = (pkg["render"] * torch.randn(pkg["render"].shape, device="cuda", generator=g)).sum() + \
+               (vol * torch.randn(vol.shape, device="cuda", generator=g)).sum()
+        loss.backward()
+        return (pkg["render"].detach(), vol.detach(), [getattr(gm, a).grad.clone() for a in groups],
+                pkg["viewspace_points"].grad.clone(), pkg["radii"].clone())
+
+    rng = np.random.default_rng(3); plain = run(False)
+    rng = np.random.default_rng(3); fused = run(True)
+    assert torch.equal(plain[4], fused[4])
+    for a, b, what in ((plain[0], fused[0], "image"), (plain[1], fused[1], "volume")):
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-9, what
+    for ga, gb, name in zip(plain[2], fused[2], groups):
+        assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max()) + 1e-9, name
+    assert float((plain[3] - fused[3]).abs().max()) <= 2e-5 * float(plain[3].abs().max()) + 1e-9
