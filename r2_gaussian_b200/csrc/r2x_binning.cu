@@ -67,6 +67,10 @@ TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
     return pl;
 }
 
+constexpr int PLAN_RUN = 32;  // consecutive tiles one thread owns per sweep of plan_kernel
+
+// One CTA.  Each thread owns PLAN_RUN consecutive tiles per sweep (1024 * PLAN_RUN tiles), so a
+// 256^3 / 8^3 grid (32768 tiles) is one sweep with one CTA-wide scan instead of 32 dependent ones.
 __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ranges, TilePlan pl) {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the lists are contiguous and tile-major: the last non-empty tile ends at R
     uint32_t Rloc = 0;
+#pragma unroll 4
     for (int t = tid; t < T; t += 1024) Rloc = max(Rloc, ranges[t].y);
     Rloc = __reduce_max_sync(0xffffffffu, Rloc);
     if (tid == 0) s_carry = 0;
@@ -86,49 +91,59 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     if (tid < 2) pl.counter[tid] = 0;
     if (tid == 2) pl.counter[2] = C;
     __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        uint32_t a = 0;
-        if (t < T) {
-            const uint2 r = ranges[t];
-            const uint32_t n = r.y - r.x;
-            a = n ? (n - 1) / C : 0u;  // extra chunks beyond the first
+    for (int sweep = 0; sweep < T; sweep += 1024 * PLAN_RUN) {
+        const int t0 = sweep + tid * PLAN_RUN;
+        uint32_t a[PLAN_RUN];
+        uint32_t mine = 0;
 #pragma unroll
-            for (int k = 0; k < PLAN_DONE_SLOTS; ++k) pl.tile_done[(size_t)t * PLAN_DONE_SLOTS + k] = 0;
+        for (int k = 0; k < PLAN_RUN; ++k) {
+            uint32_t n = 0;
+            if (t0 + k < T) {
+                const uint2 r = ranges[t0 + k];
+                n = r.y - r.x;
+            }
+            a[k] = n ? (n - 1) / C : 0u;  // extra chunks beyond the first
+            mine += a[k];
         }
-        uint32_t ia = a;
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
-            if (lane >= o) ia += ta;
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
         }
-        if (lane == 31) s_w[warp] = ia;
+        if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         if (warp == 0) {
             const uint32_t w = s_w[lane];
             uint32_t x = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t tx = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += tx;
+                const uint32_t up = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += up;
             }
             s_w[lane] = x - w;
         }
         __syncthreads();
-        const uint32_t ea = s_carry + s_w[warp] + ia - a;
-        if (t < T) {
-            pl.extra_off[t] = ea;
-            for (uint32_t c = 0; c < a; ++c)
-                if ((long long)(ea + c) < pl.max_extra) pl.extra_item[ea + c] = make_uint2((uint32_t)t, c + 1);
+        uint32_t ea = s_carry + s_w[warp] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < PLAN_RUN; ++k) {
+            const int t = t0 + k;
+            if (t < T) {
+                pl.extra_off[t] = ea;
+                for (uint32_t c = 0; c < a[k]; ++c)
+                    if ((long long)(ea + c) < pl.max_extra) pl.extra_item[ea + c] = make_uint2((uint32_t)t, c + 1);
+            }
+            ea += a[k];
         }
         __syncthreads();
-        if (tid == 1023) s_carry = ea + a;
+        if (tid == 1023) s_carry = ea;
         __syncthreads();
     }
     if (tid == 0) pl.extra_off[T] = s_carry;
 }
 
 int launch_plan(cudaStream_t st, const uint2* ranges, const TilePlan& plan) {
+    R2X_CUDA_OK(cudaMemsetAsync(plan.tile_done, 0, sizeof(uint32_t) * (size_t)plan.num_tiles * PLAN_DONE_SLOTS, st));
     plan_kernel<<<1, 1024, 0, st>>>(ranges, plan);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
@@ -306,24 +321,31 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t*
     hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan of n = 256*nb uint32 in place, one CTA of 1024 threads walking the table in coalesced
-// chunks of 4096 (one uint4 per thread) with a running carry
+// exclusive scan of n = 256*nb uint32 in place, one CTA of 1024 threads.  A thread owns SS_RUN consecutive
+// entries per sweep: it sums them (independent uint4 loads, one exposed latency), the CTA scans the 1024 sums
+// once, and the thread walks its run again (L1/L2 hits) writing the prefixes -- two sweeps for nb = 296.
+constexpr int SS_RUN = 64;
+
 __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int n) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 4096) {
-        const int i = base + tid * 4;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i + 3 < n) v = *reinterpret_cast<const uint4*>(hist + i);
-        else {
-            if (i < n) v.x = hist[i];
-            if (i + 1 < n) v.y = hist[i + 1];
-            if (i + 2 < n) v.z = hist[i + 2];
+    for (int base = 0; base < n; base += 1024 * SS_RUN) {
+        const int i0 = base + tid * SS_RUN;
+        const bool whole = i0 + SS_RUN <= n;
+        uint32_t sum = 0;
+        if (whole) {
+#pragma unroll 8
+            for (int k = 0; k < SS_RUN; k += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(hist + i0 + k);
+                sum += v.x + v.y + v.z + v.w;
+            }
+        } else {
+            for (int k = 0; k < SS_RUN; ++k)
+                if (i0 + k < n) sum += hist[i0 + k];
         }
-        const uint32_t sum = v.x + v.y + v.z + v.w;
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -343,18 +365,25 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ 
             s_warp[lane] = wi - w;
         }
         __syncthreads();
-        const uint32_t carry = s_carry;
-        uint32_t run = carry + s_warp[warp] + incl - sum;
-        uint4 o4;
-        o4.x = run; run += v.x;
-        o4.y = run; run += v.y;
-        o4.z = run; run += v.z;
-        o4.w = run; run += v.w;
-        if (i + 3 < n) *reinterpret_cast<uint4*>(hist + i) = o4;
-        else {
-            if (i < n) hist[i] = o4.x;
-            if (i + 1 < n) hist[i + 1] = o4.y;
-            if (i + 2 < n) hist[i + 2] = o4.z;
+        uint32_t run = s_carry + s_warp[warp] + incl - sum;
+        if (whole) {
+#pragma unroll 8
+            for (int k = 0; k < SS_RUN; k += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(hist + i0 + k);
+                uint4 o4;
+                o4.x = run; run += v.x;
+                o4.y = run; run += v.y;
+                o4.z = run; run += v.z;
+                o4.w = run; run += v.w;
+                *reinterpret_cast<uint4*>(hist + i0 + k) = o4;
+            }
+        } else {
+            for (int k = 0; k < SS_RUN; ++k)
+                if (i0 + k < n) {
+                    const uint32_t v = hist[i0 + k];
+                    hist[i0 + k] = run;
+                    run += v;
+                }
         }
         __syncthreads();
         if (tid == 1023) s_carry = run;

@@ -179,6 +179,19 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     stack = None
     torch.cuda.synchronize()
     t_start = time.perf_counter()
+    t_aside = 0.0     # seconds spent saving / checkpointing / evaluating (reported apart from the training steps)
+
+    class _aside:     # times a block that is not a training step; synchronises on both sides so it owns its GPU time
+        def __enter__(self):
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+        def __exit__(self, *exc):
+            nonlocal t_aside
+            torch.cuda.synchronize()
+            t_aside += time.perf_counter() - self.t0
+            return False
+
     for iteration in range(first_iter + 1, opt.iterations + 1):
         gaussians.update_learning_rate(iteration)
         if not stack:
@@ -224,24 +237,27 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                 gaussians.optimizer.zero_grad(set_to_none=True)
             if scene.model_path and (iteration in saving_iterations or iteration == opt.iterations):
                 log(f"[ITER {iteration}] Saving Gaussians")
-                if world == 1:
-                    scene.save(iteration, queryfunc)
-                else:
-                    save_sharded(scene, gaussians, iteration, queryfunc, rank)
+                with _aside():
+                    if world == 1:
+                        scene.save(iteration, queryfunc)
+                    else:
+                        save_sharded(scene, gaussians, iteration, queryfunc, rank)
             if scene.model_path and iteration in checkpoint_iterations:
                 log(f"[ITER {iteration}] Saving Checkpoint")
-                name = os.path.basename(rank_checkpoint_path(f"chkpnt{iteration}.pth", rank, world))
-                payload = (gaussians.capture(), iteration) if world == 1 else \
-                    (gaussians.capture(), iteration, {"rank": rank, "world": world})
-                torch.save(payload, os.path.join(ckpt_dir, name))
-                if world > 1:
-                    torch.distributed.barrier()      # no rank runs ahead into the next exchange while others write
+                with _aside():
+                    name = os.path.basename(rank_checkpoint_path(f"chkpnt{iteration}.pth", rank, world))
+                    payload = (gaussians.capture(), iteration) if world == 1 else \
+                        (gaussians.capture(), iteration, {"rank": rank, "world": world})
+                    torch.save(payload, os.path.join(ckpt_dir, name))
+                    if world > 1:
+                        torch.distributed.barrier()  # no rank runs ahead into the next exchange while others write
             if iteration % 100 == 0:
                 history["loss"].append((iteration, float(total)))
                 if world > 1:
                     sharded.check_peer_exchange()    # the loss read-out above synchronised anyway
             if iteration in testing_iterations:
-                history["eval"][iteration] = evaluate(scene, gaussians, pipe)
+                with _aside():
+                    history["eval"][iteration] = evaluate(scene, gaussians, pipe)
                 log(f"[ITER {iteration}] {history['eval'][iteration]}  points {gaussians.get_xyz.shape[0]}")
                 if world > 1:
                     sharded.check_peer_exchange()
@@ -249,6 +265,7 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                     write_eval_yaml(scene.model_path, iteration, history["eval"][iteration])
     torch.cuda.synchronize()
     history["seconds"] = time.perf_counter() - t_start
+    history["train_seconds"] = history["seconds"] - t_aside   # the training steps alone
     history["iterations"] = opt.iterations - first_iter
     history["gaussians"] = int(gaussians.get_xyz.shape[0])
     history["scene"], history["model"] = scene, gaussians
@@ -384,7 +401,10 @@ def main(argv=None):
         dist.destroy_process_group()
         if not rank0:
             return
-    print(json.dumps({"seconds": hist["seconds"], "ms_per_iteration": hist["seconds"] / max(hist["iterations"], 1) * 1e3,
+    n_it = max(hist["iterations"], 1)
+    print(json.dumps({"seconds": hist["seconds"], "train_seconds": hist["train_seconds"],
+                      "ms_per_iteration": hist["train_seconds"] / n_it * 1e3,       # training steps alone
+                      "ms_per_iteration_with_save_and_eval": hist["seconds"] / n_it * 1e3,
                       "gaussians": hist["gaussians"], **final}))
 
 

@@ -4,6 +4,7 @@
 (the profiled region is bracketed with cudaProfilerStart/Stop after one warm-up pass).  `--summarize <rep>` turns the
 report into profiles/-ready CSV rows: duration, DRAM bytes and GB/s, issue-slot utilisation, dominant pipe."""
 import csv
+import json
 import os
 import subprocess
 import sys
@@ -99,6 +100,17 @@ KEYS = {
 }
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                 "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        return 6486.1  # the pool's measured copy bandwidth when the driver's file is absent
+
+
+HBM_PEAK_GBPS = _hbm_peak()
+
+
 def summarize(rep, out_csv):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -124,7 +136,8 @@ def summarize(rep, out_csv):
                     v = v / 1e6 if u == "byte" else (v / 1e3 if u == "Kbyte" else (v * 1e3 if u == "Gbyte" else v))
                 vals[short] = v
         dur = vals.get("duration_us", float("nan"))
-        gbps = (vals.get("dram_read_MB", 0) + vals.get("dram_write_MB", 0)) / dur * 1e-3 * 1e6 / 1e3 if dur == dur and dur > 0 else float("nan")
+        gbps = (vals.get("dram_read_MB", 0) + vals.get("dram_write_MB", 0)) / dur * 1e3 if dur == dur and dur > 0 else float("nan")
+        vals["dram_pct_of_peak"] = gbps / HBM_PEAK_GBPS * 100.0  # of MEASURED_PEAKS.json's copy bandwidth
         pipes = {p: vals.get(p, 0) for p in ("pipe_xu_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_lsu_pct")}
         dom = max(pipes, key=pipes.get) if pipes else ""
         out.append([name] + [f"{vals.get(s, float('nan')):.4g}" for s in KEYS.values()] + [f"{gbps:.4g}", dom])

@@ -43,9 +43,12 @@ def main():
     ap.add_argument("--vox", type=int, default=160)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config4"))
     ap.add_argument("--peer_exchange", action="store_true")
+    ap.add_argument("--skip_one_gpu", action="store_true", help="only the sharded run (the 1-GPU leg was measured apart)")
+    ap.add_argument("--work", default="/tmp/r2x_config4", help="case data and model directories (large; not returned)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
-    case = os.path.join(a.out, "case_phantom")
+    os.makedirs(a.work, exist_ok=True)
+    case = os.path.join(a.work, "case_phantom")
     if not os.path.exists(os.path.join(case, "meta_data.json")):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "make_synthetic_case.py"), case, "--det",
                                str(a.det), "--vox", str(a.vox), "--train", "50", "--test", "10", "--init", str(a.init)])
@@ -54,19 +57,26 @@ def main():
               str(2 * it // 3), "--test_iterations", str(it), "--max_num_gaussians", "500000"]
     env = dict(os.environ, PYTHONPATH=ROOT)
     out = {"config": {"init_points": a.init, "detector": a.det, "volume": a.vox, "iterations": it, "gpus": a.gpus}}
-    rc1, dt1 = run([sys.executable, "-m", "r2_gaussian_b200.trainer", *common, "-m", os.path.join(a.out, "model_1gpu")],
-                   os.path.join(a.out, "train_1gpu.log"), env)
-    out["one_gpu"] = {"rc": rc1, "wall_seconds": dt1, "result": last_json(os.path.join(a.out, "train_1gpu.log"))}
+    rc1 = 0
+    if not a.skip_one_gpu:
+        rc1, dt1 = run([sys.executable, "-m", "r2_gaussian_b200.trainer", *common, "-m", os.path.join(a.work, "model_1gpu")],
+                       os.path.join(a.out, "train_1gpu.log"), env)
+        out["one_gpu"] = {"rc": rc1, "wall_seconds": dt1, "result": last_json(os.path.join(a.out, "train_1gpu.log"))}
+    if a.gpus <= 1:
+        with open(os.path.join(a.out, "summary.json"), "w") as f:
+            json.dump(out, f, indent=1)
+        print(json.dumps(out))
+        return rc1
     cmdN = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr",
             "127.0.0.1", "--master-port", "29631", "-m", "r2_gaussian_b200.trainer", *common, "-m",
-            os.path.join(a.out, f"model_{a.gpus}gpu")]
+            os.path.join(a.work, f"model_{a.gpus}gpu")]
     if a.peer_exchange:
         cmdN.append("--peer_exchange")
     rcN, dtN = run(cmdN, os.path.join(a.out, f"train_{a.gpus}gpu.log"), env)
     out["sharded"] = {"rc": rcN, "wall_seconds": dtN, "result": last_json(os.path.join(a.out, f"train_{a.gpus}gpu.log")),
                       "exchange": "peer-memory kernel" if a.peer_exchange else "NCCL all-reduce"}
-    ok = rc1 == 0 and rcN == 0 and out["one_gpu"]["result"] and out["sharded"]["result"]
-    if ok:
+    ok = rc1 == 0 and rcN == 0 and out["sharded"]["result"]
+    if ok and "one_gpu" in out and out["one_gpu"]["result"]:
         d = out["sharded"]["result"]["psnr_3d"] - out["one_gpu"]["result"]["psnr_3d"]
         out["psnr_3d_delta_db"] = d
         out["iteration_speedup"] = out["one_gpu"]["result"]["ms_per_iteration"] / out["sharded"]["result"]["ms_per_iteration"]

@@ -102,39 +102,41 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
         rb["speedup"] = rb["reference_ms"] / rb["ours_ms"]
     out["raster_fwd_bwd"] = rb
 
-    # ---- voxelizer sweep: 256^3 over 500k Gaussians (BASELINE config 4) ----
-    big = scene.make_cloud(500000, kind="init", seed=0)
-    bm = torch.tensor(big.means, device=dev); bs = torch.tensor(big.scales, device=dev)
-    br = torch.tensor(big.rotations, device=dev); bd = torch.tensor(big.density, device=dev)
-    ve = VoxelEngine(big.P, (256, 256, 256), dev, capacity=14_000_000)
-    grid = ((2.0, 2.0, 2.0), (0.0, 0.0, 0.0))
-    Rv = ve.fit(bm, bd, bs, br, *grid)
-    V = int((ve.radii[0] > 0).logical_and(ve.radii[1] > 0).logical_and(ve.radii[2] > 0).sum().item())
+    # ---- voxelizer sweep: 256^3 over 500k Gaussians (BASELINE config 4), init-like and trained-like clouds ----
     N = 256 ** 3
-    vx = {"workload": "256^3 volume query over 500k Gaussians (init-like, seed 0), forward", "num_rendered": int(Rv),
-          "visible": V, "ours_ms": timed(lambda i: ve.forward(bm, bd, bs, br, *grid), 10, 2),
-          "ours_render_kernel_ms": timed(lambda i: ve.render_only(), 10, 2)}
-    alg = 56.0 * big.P + 44.0 * V + 68.0 * Rv + 4.0 * N
-    vx["roofline"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (vx["ours_ms"] * 1e-3) / 1e9,
-                      "peak": peak_gbs, "unit": "GB/s", "frac": alg / (vx["ours_ms"] * 1e-3) / 1e9 / peak_gbs,
-                      "pair_evals": 512.0 * Rv, "pair_evals_per_s": 512.0 * Rv / (vx["ours_render_kernel_ms"] * 1e-3)}
-    if lib is not None:
-        vol = z(256, 256, 256)
-        rx = torch.zeros(big.P, dtype=torch.int32, device=dev); ry = torch.zeros_like(rx); rz = torch.zeros_like(rx)
+    grid = ((2.0, 2.0, 2.0), (0.0, 0.0, 0.0))
+    for kind, key in (("init", "voxel_256_500k"), ("trained", "voxel_256_500k_trained")):
+        big = scene.make_cloud(500000, kind=kind, seed=0)
+        bm = torch.tensor(big.means, device=dev); bs = torch.tensor(big.scales, device=dev)
+        br = torch.tensor(big.rotations, device=dev); bd = torch.tensor(big.density, device=dev)
+        ve = VoxelEngine(big.P, (256, 256, 256), dev, capacity=28_000_000)
+        Rv = ve.fit(bm, bd, bs, br, *grid)
+        V = int((ve.radii[0] > 0).logical_and(ve.radii[1] > 0).logical_and(ve.radii[2] > 0).sum().item())
+        vx = {"workload": f"256^3 volume query over 500k Gaussians ({kind}-like, seed 0), forward", "num_rendered": int(Rv),
+              "visible": V, "ours_ms": timed(lambda i: ve.forward(bm, bd, bs, br, *grid), 10, 2),
+              "ours_render_kernel_ms": timed(lambda i: ve.render_only(), 10, 2)}
+        alg = 56.0 * big.P + 44.0 * V + 68.0 * Rv + 4.0 * N
+        vx["roofline"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (vx["ours_ms"] * 1e-3) / 1e9,
+                          "peak": peak_gbs, "unit": "GB/s", "frac": alg / (vx["ours_ms"] * 1e-3) / 1e9 / peak_gbs,
+                          "pair_evals": 512.0 * Rv, "pair_evals_per_s": 512.0 * Rv / (vx["ours_render_kernel_ms"] * 1e-3)}
+        if lib is not None:
+            vol = z(256, 256, 256)
+            rx = torch.zeros(big.P, dtype=torch.int32, device=dev); ry = torch.zeros_like(rx); rz = torch.zeros_like(rx)
 
-        def ref_v(i):
-            vol.zero_()
-            lib.ref_voxel_forward(big.P, 256, 256, 256, f(2.0), f(2.0), f(2.0), f(0.0), f(0.0), f(0.0), vp(bm), vp(bd),
-                                  vp(bs), f(1.0), vp(br), None, vp(vol), vp(rx), vp(ry), vp(rz))
+            def ref_v(i):
+                vol.zero_()
+                lib.ref_voxel_forward(big.P, 256, 256, 256, f(2.0), f(2.0), f(2.0), f(0.0), f(0.0), f(0.0), vp(bm), vp(bd),
+                                      vp(bs), f(1.0), vp(br), None, vp(vol), vp(rx), vp(ry), vp(rz))
 
-        vx["reference_ms"] = timed(ref_v, 5, 1)
-        vx["speedup"] = vx["reference_ms"] / vx["ours_ms"]
-        mine = ve.forward(bm, bd, bs, br, *grid)
-        vx["parity"] = {"max_abs": float((mine - vol).abs().max()), "max_rel_to_max": float((mine - vol).abs().max() / vol.abs().max()),
-                        "radii_equal": bool(torch.equal(ve.radii[0], rx) and torch.equal(ve.radii[1], ry) and torch.equal(ve.radii[2], rz))}
-    out["voxel_256_500k"] = vx
-    del ve, bm, bs, br, bd
-    torch.cuda.empty_cache()
+            vx["reference_ms"] = timed(ref_v, 5, 1)
+            vx["speedup"] = vx["reference_ms"] / vx["ours_ms"]
+            mine = ve.forward(bm, bd, bs, br, *grid)
+            vx["parity"] = {"max_abs": float((mine - vol).abs().max()), "max_rel_to_max": float((mine - vol).abs().max() / vol.abs().max()),
+                            "radii_equal": bool(torch.equal(ve.radii[0], rx) and torch.equal(ve.radii[1], ry) and torch.equal(ve.radii[2], rz))}
+            del vol, rx, ry, rz, mine
+        out[key] = vx
+        del ve, bm, bs, br, bd
+        torch.cuda.empty_cache()
 
     # ---- TV crop: 32^3 sub-volume of the 100k cloud, forward + backward ----
     dV = torch.randn(32, 32, 32, device=dev, generator=torch.Generator(dev).manual_seed(1))
