@@ -104,6 +104,12 @@ DirectBin carve_directbin(const void* image_buf, int P, int tiles) {
     return directbin_view(p, P, tiles);
 }
 
+TwoLevel carve_two_level(const void* image_buf, int P, int gx, int gy, int gz, const BinningView& bv) {
+    const int tiles = gx * gy * gz;
+    char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2)) + plan_bytes(tiles);
+    return two_level_view(p, P, gx, gy, gz, bv);
+}
+
 // sorted position -> tile id through the ranges (direct binning keeps no per-instance tile array)
 __global__ void export_keys_ranges_kernel(long long R, const uint32_t* d_total, const uint2* ranges, int T,
                                           const uint32_t* point_list, const float* depth, int depth_stride,
@@ -324,6 +330,7 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
                         "with cov3D_precomp; the reference dereferences scales unconditionally, VOX/forward.cu:137)");
     if (!cov3D_precomp && !rotations) return fail_msg(R2X_ERR_INVALID, "r2x_voxel_forward: need rotations or cov3D_precomp");
     const bool direct = direct_ok(tiles);
+    const bool two_level = two_level_ok(vg.gx, vg.gy, vg.gz);   // more tiles than the direct table holds
     DirectBin db{};
     if (direct) {
         db = carve_directbin(image_buf, P, tiles);
@@ -356,6 +363,11 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
     if (direct) {
         R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv, vg.gx,
                                    vg.gy, s.status));
+    } else if (two_level) {
+        status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
+        const TwoLevel tl = carve_two_level(image_buf, P, vg.gx, vg.gy, vg.gz, bv);
+        R2X_TRY(launch_two_level(st, P, s.geom.cube, s.geom.tiles_touched, vg.gx, vg.gy, vg.gz, s.status, tl, bv, ranges,
+                                 plan));
     } else {
         status_kernel<<<1, 1, 0, st>>>(s.status, capacity, status_dev);
         R2X_TRY(bin_instances(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, vg.gx, vg.gy, tiles, s.status,
@@ -386,7 +398,8 @@ size_t r2x_raster_image_bytes(int P, int W, int H) {
 size_t r2x_voxel_geom_bytes(int P) { return voxel_geom_bytes(P); }
 size_t r2x_voxel_image_bytes(int P, int nx, int ny, int nz) {
     size_t t = (size_t)((nx + 7) / 8) * ((ny + 7) / 8) * ((nz + 7) / 8);
-    return al(t * sizeof(uint2)) + plan_bytes((int)t) + (direct_ok((int)t) ? directbin_bytes(P, (int)t) : 0) + 1024;
+    return al(t * sizeof(uint2)) + plan_bytes((int)t) + (direct_ok((int)t) ? directbin_bytes(P, (int)t) : 0) +
+           two_level_bytes(P, (nx + 7) / 8, (ny + 7) / 8, (nz + 7) / 8) + 1024;
 }
 size_t r2x_binning_bytes(long long R) { return binning_bytes(R); }
 size_t r2x_raster_bwd_scratch_bytes(long long R) { return al((size_t)(R > 0 ? R : 1) * 32) + 256; }
@@ -553,7 +566,8 @@ int r2x_voxel_backward(void* stream, int P, long long R, int nx, int ny, int nz,
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
     const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
-    const uint32_t* inst_pos = direct_ok(vg.gx * vg.gy * vg.gz) ? nullptr : bv.inst_pos;
+    // direct and two-level binning keep no per-instance slot array: the slots are derived (emission_slot())
+    const uint32_t* inst_pos = (direct_ok(vg.gx * vg.gy * vg.gz) || two_level_ok(vg.gx, vg.gy, vg.gz)) ? nullptr : bv.inst_pos;
     if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, inst_pos, plan, R, dL_dvol, inst_grad));
     R2X_TRY(debug_sync(st, debug, "voxel render backward"));
     R2X_TRY(launch_voxel_gauss_bwd(st, P, radii_x, radii_y, radii_z, scales, scale_modifier, rotations, cov3D_precomp, vg,
@@ -576,7 +590,7 @@ int r2x_voxel_export(void* stream, int P, int nx, int ny, int nz, long long R, c
     if (ranges) export_ranges_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>((int)tiles, (const uint2*)al((size_t)image_buf), ranges);
     if (R > 0 && (keys || point_list)) {
         BinningView bv = binning_view((void*)binning_buf, R);
-        if (direct_ok((int)tiles)) {
+        if (direct_ok((int)tiles) || two_level_ok((nx + 7) / 8, (ny + 7) / 8, (nz + 7) / 8)) {
             export_keys_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(
                 R, s.status, (const uint2*)al((size_t)image_buf), (int)tiles, bv.point_list, reinterpret_cast<const float*>(s.geom.rec) + 13, 16, keys, point_list);
         } else {

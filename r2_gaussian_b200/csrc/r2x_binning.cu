@@ -93,18 +93,16 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     __syncthreads();
     for (int sweep = 0; sweep < T; sweep += 1024 * PLAN_RUN) {
         const int t0 = sweep + tid * PLAN_RUN;
-        uint32_t a[PLAN_RUN];
+        // extra chunks (beyond the first) of tile t; evaluated twice (sum, then placement) instead of kept in 32 registers
+        auto extra_chunks = [&](int t) -> uint32_t {
+            if (t >= T) return 0u;
+            const uint2 r = ranges[t];
+            const uint32_t n = r.y - r.x;
+            return n ? (n - 1) / C : 0u;
+        };
         uint32_t mine = 0;
-#pragma unroll
-        for (int k = 0; k < PLAN_RUN; ++k) {
-            uint32_t n = 0;
-            if (t0 + k < T) {
-                const uint2 r = ranges[t0 + k];
-                n = r.y - r.x;
-            }
-            a[k] = n ? (n - 1) / C : 0u;  // extra chunks beyond the first
-            mine += a[k];
-        }
+#pragma unroll 8
+        for (int k = 0; k < PLAN_RUN; ++k) mine += extra_chunks(t0 + k);
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -125,15 +123,16 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
         }
         __syncthreads();
         uint32_t ea = s_carry + s_w[warp] + incl - mine;
-#pragma unroll
+#pragma unroll 4
         for (int k = 0; k < PLAN_RUN; ++k) {
             const int t = t0 + k;
+            const uint32_t a = extra_chunks(t);
             if (t < T) {
                 pl.extra_off[t] = ea;
-                for (uint32_t c = 0; c < a[k]; ++c)
+                for (uint32_t c = 0; c < a; ++c)
                     if ((long long)(ea + c) < pl.max_extra) pl.extra_item[ea + c] = make_uint2((uint32_t)t, c + 1);
             }
-            ea += a[k];
+            ea += a;
         }
         __syncthreads();
         if (tid == 1023) s_carry = ea;

@@ -162,6 +162,30 @@ __device__ __forceinline__ void block_tile_histogram(uint32_t* hist_s, const Dir
     }
 }
 
+// ---- two-level direct binning (voxel grids with more than DIRECT_MAX_TILES tiles; r2x_binning2.cu) --------------
+struct TwoLevel {
+    int gx1, gy1, gz1, T1;      // supertile grid (4 x 4 x 4 tiles per supertile)
+    uint16_t* cube1;            // [P][6] supertile cube of every Gaussian
+    uint32_t* tiles1;           // [P]    supertiles touched
+    uint32_t* offsets1;         // [P]    inclusive scan of tiles1 (direct_fill)
+    uint32_t* status1;          // [4]    0: R1, 1: level-1 overflow, 2: scratch total of the tile scan
+    uint2* ranges1;             // [T1]   supertile lists
+    TilePlan plan1;             // level-2 work items = (supertile, chunk of <= 256 entries)
+    DirectBin db1;              // level-1 table
+    uint32_t* list1;            // [R1]   Gaussian ids, supertile-major, ascending       (binning buffer: keys[0])
+    uint32_t* table2a;          // [T1][64]  per-tile counts / prefixes of every supertile's first item
+    uint32_t* table2b;          // [E1][64]  ... of the extra items                         (binning buffer: keys[1])
+    uint32_t* tile_count;       // [T]
+    uint32_t* tile_incl;        // [T]    inclusive scan of tile_count in tile-id order
+    void* scan_state;
+};
+bool two_level_ok(int gx, int gy, int gz);   // false when the grid fits the direct table, is too large, or R2X_VOXEL_BINNING=radix
+size_t two_level_bytes(int P, int gx, int gy, int gz);
+TwoLevel two_level_view(void* buf, int P, int gx, int gy, int gz, const BinningView& bv);
+int launch_two_level(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, int gx, int gy, int gz,
+                     const uint32_t* status, const TwoLevel& tl, const BinningView& bv, uint2* ranges,
+                     const TilePlan& plan);
+
 int launch_direct_scan(cudaStream_t st, const DirectBin& db, uint32_t* status, long long capacity,
                        uint32_t* status_out);
 int launch_direct_fill(cudaStream_t st, int P, const uint16_t* cube, const uint32_t* tiles_touched, uint32_t* offsets,
