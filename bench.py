@@ -54,6 +54,15 @@ METRIC = "projections_per_sec"
 UNIT = "projections/s"
 
 
+_T0 = time.time()
+
+
+def trace(msg: str) -> None:
+    """Stage markers on stderr when R2X_BENCH_TRACE is set (stdout carries the one JSON line only)."""
+    if os.environ.get("R2X_BENCH_TRACE"):
+        print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -528,12 +537,14 @@ def run_ours(args, rank, world, local_rank):
                           "summed over ranks on the device, pinned host inputs, image read back each step")
         result["e2e"] = e2e
 
+    trace("headline measured")
     if rank == 0 and world == 1 and not args.no_secondary:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import secondary
         del eng
         torch.cuda.empty_cache()
-        result["secondary"] = secondary.measure(dev, peak)
+        result["secondary"] = secondary.measure(dev, peak, trace=trace)
+        trace("secondary done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cloud, views, 2)
         result["cpu_baseline_torch"] = cpu_baseline_torch(cloud, views, 3)

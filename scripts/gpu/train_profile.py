@@ -66,6 +66,20 @@ def main():
     t_wall = time.perf_counter() - t0
     out = {"wall_ms_per_iteration": t_wall / n * 1e3, "host_enqueue_ms_per_iteration": t_enq / n * 1e3,
            "fused_activations": os.environ.get("R2X_FUSED_ACTIVATIONS", "default")}
+    if os.environ.get("TRAIN_CPROFILE"):      # where the HOST time of an iteration goes, Python frames included
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(n):
+            train_iter()
+        pr.disable()
+        torch.cuda.synchronize()
+        st = pstats.Stats(pr)
+        rows = sorted(st.stats.items(), key=lambda kv: kv[1][3], reverse=True)[:40]
+        out["cprofile_top_cumulative"] = [
+            {"fn": f"{os.path.basename(k[0])}:{k[1]}:{k[2]}", "calls_per_iteration": v[1] / n,
+             "self_us_per_iteration": v[2] / n * 1e6, "cum_us_per_iteration": v[3] / n * 1e6} for k, v in rows]
     from torch.profiler import ProfilerActivity, profile
     m = 20
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:

@@ -24,7 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
+def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False, trace=lambda msg: None) -> dict:
     import torch
 
     import bench
@@ -101,6 +101,7 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
         rb["reference_ms"] = timed(ref_fb, 10, 2)
         rb["speedup"] = rb["reference_ms"] / rb["ours_ms"]
     out["raster_fwd_bwd"] = rb
+    trace("secondary: raster forward + backward")
 
     # ---- voxelizer sweep: 256^3 over 500k Gaussians (BASELINE config 4), init-like and trained-like clouds ----
     N = 256 ** 3
@@ -135,6 +136,7 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
                             "radii_equal": bool(torch.equal(ve.radii[0], rx) and torch.equal(ve.radii[1], ry) and torch.equal(ve.radii[2], rz))}
             del vol, rx, ry, rz, mine
         out[key] = vx
+        trace(f"secondary: {key} (R = {int(Rv)})")
         del ve, bm, bs, br, bd
         torch.cuda.empty_cache()
 
@@ -166,6 +168,7 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False) -> dict:
         tv["speedup"] = tv["reference_ms"] / tv["ours_ms"]
     out["tv_crop_32"] = tv
 
+    trace("secondary: TV crop")
     # ---- one training iteration on the headline scene ----
     scanner = scene.cone_beam_scanner(512)
     cams = [scene.camera_from_view(vw, device=dev) for vw in scene.make_views(scanner, 8)]
