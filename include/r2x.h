@@ -188,6 +188,18 @@ typedef struct r2x_adam_group {
 } r2x_adam_group;
 int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
                   long long step);
+/* The same step with the gradient of group i taken as groups[i].grad + grads2[i] (grads2 or an entry may be NULL): what
+ * autograd's accumulation of the render() and query() backward passes amounts to (train.py:141), without the
+ * accumulation kernels.  guard0 / guard1 (either may be NULL) are the {num_rendered, overflow} status words of the
+ * asynchronous forwards this step's gradients came from: if any reports an overflow the launch changes NOTHING, so an
+ * iteration whose speculative forward ran out of instance capacity can simply be repeated. */
+int r2x_adam_step_sum(void* stream, int ngroups, const r2x_adam_group* groups, const float* const* grads2, double beta1,
+                      double beta2, double eps, long long step, const uint32_t* guard0, const uint32_t* guard1);
+/* Densification statistics of one iteration in one launch (train.py:150-156, gaussian_model.py:552-556): for the visible
+ * Gaussians (radii > 0)  max_radii2D = max(max_radii2D, radii),  xyz_gradient_accum += |dL_dmean2D.xy|,  denom += 1.
+ * dL_dmean2D is [P,3]; the other arrays [P] float32.  Guards as above. */
+int r2x_densify_stats(void* stream, int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
+                      float* xyz_gradient_accum, float* denom, const uint32_t* guard0, const uint32_t* guard1);
 
 /* ---- folded parameter activations ------------------------------------------ */
 /* The reference applies softplus (density), a bounded sigmoid or exp (scale) and normalize (rotation) as separate torch

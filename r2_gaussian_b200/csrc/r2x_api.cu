@@ -11,7 +11,9 @@
 
 namespace r2x {
 int launch_adam(cudaStream_t st, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
-                long long step);
+                long long step, const float* const* grads2, const uint32_t* guard0, const uint32_t* guard1);
+int launch_densify_stats(cudaStream_t st, int P, const int* radii, const float* grad2d, float* max_radii, float* accum,
+                         float* denom, const uint32_t* guard0, const uint32_t* guard1);
 
 static thread_local std::string g_err;
 static thread_local Activation g_act = {0, 0, 0.f, 0.f};
@@ -692,7 +694,21 @@ int r2x_tv3d_loss(void* stream, int nx, int ny, int nz, const float* vol, int re
 int r2x_adam_step(void* stream, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
                   long long step) {
     if (ngroups > 0 && !groups) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: null groups");
-    return r2x::launch_adam((cudaStream_t)stream, ngroups, groups, beta1, beta2, eps, step);
+    return r2x::launch_adam((cudaStream_t)stream, ngroups, groups, beta1, beta2, eps, step, nullptr, nullptr, nullptr);
+}
+
+int r2x_adam_step_sum(void* stream, int ngroups, const r2x_adam_group* groups, const float* const* grads2, double beta1,
+                      double beta2, double eps, long long step, const uint32_t* guard0, const uint32_t* guard1) {
+    if (ngroups > 0 && !groups) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step_sum: null groups");
+    return r2x::launch_adam((cudaStream_t)stream, ngroups, groups, beta1, beta2, eps, step, grads2, guard0, guard1);
+}
+
+int r2x_densify_stats(void* stream, int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
+                      float* xyz_gradient_accum, float* denom, const uint32_t* guard0, const uint32_t* guard1) {
+    if (P > 0 && (!radii || !dL_dmean2D || !max_radii2D || !xyz_gradient_accum || !denom))
+        return fail_msg(R2X_ERR_INVALID, "r2x_densify_stats: null pointer");
+    return r2x::launch_densify_stats((cudaStream_t)stream, P, radii, dL_dmean2D, max_radii2D, xyz_gradient_accum, denom,
+                                     guard0, guard1);
 }
 
 }  // extern "C"

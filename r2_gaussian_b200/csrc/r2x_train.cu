@@ -289,15 +289,19 @@ int launch_tv3d(cudaStream_t st, int nx, int ny, int nz, const float* vol, int r
 // ------------------------------------------------------------------------------------------------
 struct AdamPack {
     r2x_adam_group g[R2X_ADAM_MAX_GROUPS];
+    const float* grad2[R2X_ADAM_MAX_GROUPS];   // optional second gradient source, summed with g.grad (null = none)
+    const uint32_t* guard[2];                  // optional {count, overflow} status words: any overflow -> no update
     int n;
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamPack pk, float one_minus_b1, float beta2, float one_minus_b2,
                                                    float eps, float inv_bc1, float inv_sqrt_bc2) {
+    if ((pk.guard[0] && pk.guard[0][1]) || (pk.guard[1] && pk.guard[1][1])) return;
     const r2x_adam_group gr = pk.g[blockIdx.y];
+    const float* __restrict__ g2 = pk.grad2[blockIdx.y];
     const float step_size = gr.lr * inv_bc1;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < gr.numel; i += (long long)gridDim.x * 256) {
-        const float g = gr.grad[i];
+        const float g = g2 ? gr.grad[i] + g2[i] : gr.grad[i];
         float m = gr.exp_avg[i], v = gr.exp_avg_sq[i];
         m = fmaf(one_minus_b1, g - m, m);
         v = fmaf(one_minus_b2, g * g, beta2 * v);
@@ -309,15 +313,18 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamPack pk, float one_minus_
 }
 
 int launch_adam(cudaStream_t st, int ngroups, const r2x_adam_group* groups, double beta1, double beta2, double eps,
-                long long step) {
+                long long step, const float* const* grads2, const uint32_t* guard0, const uint32_t* guard1) {
     if (ngroups < 0 || ngroups > R2X_ADAM_MAX_GROUPS) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: too many groups");
     if (step < 1) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: step counts from 1");
     if (ngroups == 0) return 0;
     AdamPack pk{};
     pk.n = ngroups;
+    pk.guard[0] = guard0;
+    pk.guard[1] = guard1;
     long long maxn = 0;
     for (int i = 0; i < ngroups; ++i) {
         pk.g[i] = groups[i];
+        pk.grad2[i] = grads2 ? grads2[i] : nullptr;
         if (groups[i].numel < 0) return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: negative numel");
         if (groups[i].numel > 0 && (!groups[i].param || !groups[i].grad || !groups[i].exp_avg || !groups[i].exp_avg_sq))
             return fail_msg(R2X_ERR_INVALID, "r2x_adam_step: null pointer");
@@ -331,6 +338,34 @@ int launch_adam(cudaStream_t st, int ngroups, const r2x_adam_group* groups, doub
     adam_kernel<<<dim3((unsigned)nb, (unsigned)ngroups), 256, 0, st>>>(
         pk, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)(1.0 / bc1),
         (float)(1.0 / sqrt(bc2)));
+    R2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Densification statistics of one iteration (train.py:150-156 + gaussian_model.py:552-556) in one launch:
+//   visible = radii > 0;  max_radii2D = max(max_radii2D, radii) | visible;  accum += |dL/dmean2D (x, y)| | visible;
+//   denom += 1 | visible.   The guards are the forwards' {count, overflow} words: an overflowed iteration changes nothing.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) densify_stats_kernel(int P, const int* __restrict__ radii,
+                                                            const float* __restrict__ grad2d, float* __restrict__ max_radii,
+                                                            float* __restrict__ accum, float* __restrict__ denom,
+                                                            const uint32_t* guard0, const uint32_t* guard1) {
+    if ((guard0 && guard0[1]) || (guard1 && guard1[1])) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P) return;
+    const int r = radii[g];
+    if (r <= 0) return;
+    max_radii[g] = fmaxf(max_radii[g], (float)r);
+    const float gx = grad2d[3 * (size_t)g], gy = grad2d[3 * (size_t)g + 1];
+    accum[g] += sqrtf(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+    denom[g] += 1.0f;
+}
+
+int launch_densify_stats(cudaStream_t st, int P, const int* radii, const float* grad2d, float* max_radii, float* accum,
+                         float* denom, const uint32_t* guard0, const uint32_t* guard1) {
+    if (P <= 0) return 0;
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii, grad2d, max_radii, accum, denom, guard0, guard1);
     R2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
