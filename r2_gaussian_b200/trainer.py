@@ -32,7 +32,7 @@ from .dataset import Scene
 from .gaussian_model import GaussianModel
 from .metrics import metric_proj, metric_vol
 from .render_query import query, render
-from . import sharded
+from . import sharded, train_step
 from .sharded import gather_point_cloud, shard_init_points, world_info
 
 
@@ -177,6 +177,10 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
         os.makedirs(ckpt_dir, exist_ok=True)
     history = {"eval": {}, "loss": []}
     stack = None
+    native = None
+    if train_step.enabled() and not getattr(pipe, "debug", False) and not getattr(pipe, "compute_cov3D_python", False):
+        native = train_step.NativeTrainStep(gaussians, opt.lambda_dssim, opt.lambda_tv if use_tv else 0.0, tv_n,
+                                            [float(v) for v in tv_s])
     torch.cuda.synchronize()
     t_start = time.perf_counter()
     t_aside = 0.0     # seconds spent saving / checkpointing / evaluating (reported apart from the training steps)
@@ -198,43 +202,63 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
             stack = scene.getTrainCameras().copy()
         cam = stack.pop(random.randint(0, len(stack) - 1))
 
-        pkg = render(cam, gaussians, pipe)
-        gt = cam.original_image.cuda()
-        loss = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)
-        total = loss["total"]
+        densify_due = iteration < opt.densify_until_iter and iteration > opt.densify_from_iter \
+            and iteration % opt.densification_interval == 0
+        centre = None
         if use_tv:
             centre = (bbox_cpu[0] + tv_s / 2) + (bbox_cpu[1] - tv_s - bbox_cpu[0]) * torch.rand(3)
-            vol = query(gaussians, centre, tv_n, tv_s, pipe)["vol"]
-            total = total + opt.lambda_tv * losses.tv_3d_loss(vol, reduction="mean")
-        try:
-            total.backward()
-        except CapacityOverflow:
-            # a speculative forward (no host sync) ran out of instance capacity: its image was all zeros and this
-            # step's gradients are void.  The capacity hint has been raised; redo the step with the same camera.
-            gaussians.optimizer.zero_grad(set_to_none=True)
+        if native is not None and gaussians.get_xyz.shape[0] > 0:
+            # fixed launch sequence, no autograd (train_step.py).  At a densification iteration the reference's
+            # optimizer.step() comes AFTER the tensors were replaced and therefore applies nothing (their .grad is None,
+            # train.py:158-176): the same here.
+            gt = cam.original_image.cuda()
+            native(cam, gt, centre, apply_update=(iteration < opt.iterations) and not densify_due)
+            total = None
+            with torch.no_grad():
+                if densify_due:
+                    native.flush()
+                    gaussians.densify_and_prune(opt.densify_grad_threshold, opt.density_min_threshold, opt.max_screen_size,
+                                                ds["max_scale"], opt.max_num_gaussians, ds["densify_scale_threshold"], bbox)
+        else:
             pkg = render(cam, gaussians, pipe)
-            total = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)["total"]
+            gt = cam.original_image.cuda()
+            loss = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)
+            total = loss["total"]
             if use_tv:
-                total = total + opt.lambda_tv * losses.tv_3d_loss(query(gaussians, centre, tv_n, tv_s, pipe)["vol"],
-                                                                  reduction="mean")
-            total.backward()
+                vol = query(gaussians, centre, tv_n, tv_s, pipe)["vol"]
+                total = total + opt.lambda_tv * losses.tv_3d_loss(vol, reduction="mean")
+            try:
+                total.backward()
+            except CapacityOverflow:
+                # a speculative forward (no host sync) ran out of instance capacity: its image was all zeros and this
+                # step's gradients are void.  The capacity hint has been raised; redo the step with the same camera.
+                gaussians.optimizer.zero_grad(set_to_none=True)
+                pkg = render(cam, gaussians, pipe)
+                total = losses.image_loss(pkg["render"], gt, lambda_dssim=opt.lambda_dssim)["total"]
+                if use_tv:
+                    total = total + opt.lambda_tv * losses.tv_3d_loss(query(gaussians, centre, tv_n, tv_s, pipe)["vol"],
+                                                                      reduction="mean")
+                total.backward()
+            with torch.no_grad():
+                gaussians.update_max_radii(pkg["radii"], pkg["visibility_filter"])
+                gaussians.add_densification_stats(pkg["viewspace_points"], pkg["visibility_filter"])
+                if densify_due:
+                    gaussians.densify_and_prune(opt.densify_grad_threshold, opt.density_min_threshold, opt.max_screen_size,
+                                                ds["max_scale"], opt.max_num_gaussians, ds["densify_scale_threshold"], bbox)
 
         with torch.no_grad():
-            gaussians.update_max_radii(pkg["radii"], pkg["visibility_filter"])
-            gaussians.add_densification_stats(pkg["viewspace_points"], pkg["visibility_filter"])
-            if iteration < opt.densify_until_iter and iteration > opt.densify_from_iter \
-                    and iteration % opt.densification_interval == 0:
-                gaussians.densify_and_prune(opt.densify_grad_threshold, opt.density_min_threshold, opt.max_screen_size,
-                                            ds["max_scale"], opt.max_num_gaussians, ds["densify_scale_threshold"], bbox)
             # sharded: an EMPTY SHARD is fine and keeps going through the P == 0 path; the run stops -- on every rank at
             # once, so nobody is left waiting in a collective -- only when the whole cloud is gone (the count can only
             # change at a densification step, which is where the all-reduce is paid)
             if (world == 1 and gaussians.get_density.shape[0] == 0) or \
                     (world > 1 and iteration % opt.densification_interval == 0 and total_gaussians(gaussians, world) == 0):
                 raise ValueError("No Gaussian left. Change adaptive control hyperparameters!")
-            if iteration < opt.iterations:
+            if total is not None and iteration < opt.iterations:
                 gaussians.optimizer.step()
                 gaussians.optimizer.zero_grad(set_to_none=True)
+            if native is not None and (iteration in saving_iterations or iteration in checkpoint_iterations or
+                                       iteration in testing_iterations or iteration == opt.iterations):
+                native.flush()       # the last enqueued iteration is checked (and repeated if it had overflowed)
             if scene.model_path and (iteration in saving_iterations or iteration == opt.iterations):
                 log(f"[ITER {iteration}] Saving Gaussians")
                 with _aside():
@@ -252,7 +276,7 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                     if world > 1:
                         torch.distributed.barrier()  # no rank runs ahead into the next exchange while others write
             if iteration % 100 == 0:
-                history["loss"].append((iteration, float(total)))
+                history["loss"].append((iteration, float(total) if total is not None else native.total_loss()))
                 if world > 1:
                     sharded.check_peer_exchange()    # the loss read-out above synchronised anyway
             if iteration in testing_iterations:
@@ -263,6 +287,9 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
                     sharded.check_peer_exchange()
                 if scene.model_path and rank == 0:
                     write_eval_yaml(scene.model_path, iteration, history["eval"][iteration])
+    if native is not None:
+        native.flush()
+        history["repeated_iterations"] = native.repeats
     torch.cuda.synchronize()
     history["seconds"] = time.perf_counter() - t_start
     history["train_seconds"] = history["seconds"] - t_aside   # the training steps alone

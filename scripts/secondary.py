@@ -212,9 +212,34 @@ def measure(dev=None, peak_gbs: float = 6486.1, quick: bool = False, trace=lambd
     for k in range(n_it):
         train_iter(k)
     sync()
+    autograd_ms = (time.perf_counter() - t0) / n_it * 1e3
+    # the same iteration as a fixed launch sequence (train_step.NativeTrainStep: no autograd graph, no allocation)
+    from r2_gaussian_b200.train_step import NativeTrainStep
+    native = NativeTrainStep(gm, 0.25, 0.05, [32, 32, 32], [0.25, 0.25, 0.25])
+
+    def native_iter():
+        i = it[0] = it[0] + 1
+        gm.update_learning_rate(i)
+        native(cams[i % 8], gts[i % 8], (0.1, 0.0, -0.1))
+
+    for k in range(5):
+        native_iter()
+    native.flush()
+    sync()
+    n_nat = 20 if quick else 200
+    t0 = time.perf_counter()
+    for k in range(n_nat):
+        native_iter()
+    native.flush()
+    sync()
+    native_ms = (time.perf_counter() - t0) / n_nat * 1e3
     out["train_iteration"] = {"workload": "100k Gaussians, 512x512: render + fused L1/D-SSIM + 32^3 TV crop query + backward + "
-                                          "fused Adam + densification statistics (GaussianModel / render() / query())",
-                              "ours_ms_wall": (time.perf_counter() - t0) / n_it * 1e3}
+                                          "fused Adam + densification statistics",
+                              "ours_ms_wall": native_ms, "api": "train_step.NativeTrainStep (what trainer.py runs)",
+                              "autograd_path_ms_wall": autograd_ms,
+                              "autograd_path_api": "GaussianModel / render() / query() / losses / FusedAdam behind autograd",
+                              "repeated_iterations": native.repeats}
+    trace("secondary: training iteration")
     return out
 
 

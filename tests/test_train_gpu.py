@@ -528,3 +528,96 @@ def test_folded_activations_match_the_torch_activations(bounded, monkeypatch):
     for ga, gb, name in zip(plain[2], fused[2], groups):
         assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max()) + 1e-9, name
     assert float((plain[3] - fused[3]).abs().max()) <= 2e-5 * float(plain[3].abs().max()) + 1e-9
+
+
+def _train_inputs(n_cams=4, det=128):
+    from r2_gaussian_b200 import scene
+    scanner = scene.cone_beam_scanner(det, 64)
+    cams = [scene.camera_from_view(scene.make_view(scanner, 0.3 + 0.9 * k)) for k in range(n_cams)]
+    g = torch.Generator("cuda").manual_seed(9)
+    gts = [torch.rand((1, det, det), device="cuda", generator=g) * 0.5 for _ in cams]
+    centres = [(0.1 * k - 0.15, 0.05 * k, -0.1 + 0.07 * k) for k in range(n_cams)]
+    return cams, gts, centres
+
+
+@pytest.mark.parametrize("use_tv", [True, False])
+def test_native_train_step_is_the_autograd_iteration(use_tv):
+    """NativeTrainStep (fixed launch sequence, guarded Adam / statistics, no autograd) against the same iteration through
+    render() / query() / the fused losses / autograd / FusedAdam: parameters and Adam moments bit for bit."""
+    from r2_gaussian_b200 import losses
+    from r2_gaussian_b200.render_query import query, render
+    from r2_gaussian_b200.train_step import NativeTrainStep
+    pipe = types.SimpleNamespace(compute_cov3D_python=False, debug=False)
+    cams, gts, centres = _train_inputs()
+    lam_d, lam_tv, n_it = 0.25, 0.05, 7
+    tv_n, tv_s = [32, 32, 32], [0.5, 0.5, 0.5]
+    a, _, _ = _make_model(n=5000, seed=11)
+    b, _, _ = _make_model(n=5000, seed=11)
+    step = NativeTrainStep(b, lam_d, lam_tv if use_tv else 0.0, tv_n, tv_s)
+    for i in range(1, n_it + 1):
+        k = i % len(cams)
+        a.update_learning_rate(i); b.update_learning_rate(i)
+        pkg = render(cams[k], a, pipe)
+        total = losses.image_loss(pkg["render"], gts[k], lam_d)["total"]
+        if use_tv:
+            total = total + lam_tv * losses.tv_3d_loss(query(a, centres[k], tv_n, tv_s, pipe)["vol"], "mean")
+        total.backward()
+        with torch.no_grad():
+            a.update_max_radii(pkg["radii"], pkg["visibility_filter"])
+            a.add_densification_stats(pkg["viewspace_points"], pkg["visibility_filter"])
+        a.optimizer.step()
+        a.optimizer.zero_grad(set_to_none=True)
+        res = step(cams[k], gts[k], centres[k])
+        if i == n_it:
+            assert abs(step.total_loss() - float(total)) <= 1e-6 * abs(float(total))
+            assert torch.equal(res["radii"], pkg["radii"])
+    step.flush()
+    assert step.repeats == 0
+    for name in ("_xyz", "_density", "_scaling", "_rotation"):
+        pa, pb = getattr(a, name), getattr(b, name)
+        assert torch.equal(pa, pb), name
+        sa, sb = a.optimizer.state[pa], b.optimizer.state[pb]
+        assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"]), name
+        assert float(sa["step"]) == float(sb["step"]) == n_it
+    assert torch.equal(a.max_radii2D, b.max_radii2D)
+    assert torch.equal(a.denom, b.denom)
+    assert float((a.xyz_gradient_accum - b.xyz_gradient_accum).abs().max()) <= 1e-6 * float(a.xyz_gradient_accum.abs().max())
+
+
+def test_native_train_step_repeats_an_overflowed_iteration():
+    """A speculative forward that runs out of instance capacity changes nothing on the device (guarded launches); the
+    step notices one call late, raises the capacity and repeats the iteration: same result as without the overflow."""
+    from r2_gaussian_b200 import _C
+    from r2_gaussian_b200.train_step import NativeTrainStep
+    cams, gts, centres = _train_inputs(n_cams=2)
+    a, _, _ = _make_model(n=5000, seed=13)
+    b, _, _ = _make_model(n=5000, seed=13)
+    sa = NativeTrainStep(a, 0.25, 0.05, [32, 32, 32], [0.5, 0.5, 0.5])
+    sb = NativeTrainStep(b, 0.25, 0.05, [32, 32, 32], [0.5, 0.5, 0.5])
+    for i in (1, 2):
+        a.update_learning_rate(i); sa(cams[i % 2], gts[i % 2], centres[i % 2])
+    sa.flush()
+    b.update_learning_rate(1); sb(cams[1], gts[1], centres[1]); sb.flush()
+    # starve b's second iteration: a capacity of one page of instances for both forwards
+    sb.cap_r, sb.cap_v = 4096, 4096
+    lib = sb.lib
+    sb.binning_r = torch.empty(lib.r2x_binning_bytes(4096), dtype=torch.uint8, device="cuda")
+    sb.scratch_r = torch.empty(lib.r2x_raster_bwd_scratch_bytes(4096), dtype=torch.uint8, device="cuda")
+    sb.binning_v = torch.empty(lib.r2x_binning_bytes(4096), dtype=torch.uint8, device="cuda")
+    sb.scratch_v = torch.empty(lib.r2x_voxel_bwd_scratch_bytes(4096), dtype=torch.uint8, device="cuda")
+    saved = dict(_C._Workspace.hints)
+    _C._Workspace.hints[sb.key_r] = 1; _C._Workspace.hints[sb.key_v] = 1
+    sb._provision = lambda: None                       # keep the starved buffers for the next call
+    b.update_learning_rate(2)
+    before = b._xyz.clone()
+    sb(cams[0], gts[0], centres[0])
+    torch.cuda.synchronize()
+    assert torch.equal(before, b._xyz)                  # guarded: the overflowed iteration changed nothing
+    del sb._provision                                   # normal provisioning again
+    sb.cap_r = sb.cap_v = 0
+    sb.flush()                                          # notices the overflow, repeats the iteration
+    assert sb.repeats == 1
+    _C._Workspace.hints.update({k: v for k, v in saved.items() if k in (sb.key_r, sb.key_v)})
+    for name in ("_xyz", "_density", "_scaling", "_rotation"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert float(a.optimizer.state[a._xyz]["step"]) == float(b.optimizer.state[b._xyz]["step"]) == 2
