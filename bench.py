@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` block (other BASELINE configs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the `parity` block (timed views vs the reference's kernels)")
+    ap.add_argument("--cpu-baseline-child", default=None, choices=["port", "torch"], help=argparse.SUPPRESS)
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank partial images are summed (NVLink peer-memory kernel | NCCL)")
     return ap.parse_args()
@@ -195,10 +196,43 @@ def timed_steps(step_fn, steps, warmup, flush_buf, stream_sync):
     return [s.elapsed_time(e) for s, e in zip(starts, stops)]
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota (a container limited
+    to a few cores still reports every core of the box in os.cpu_count(); OpenMP / torch threads beyond the quota spin)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def guarded_cpu_baseline(args, kind: str, limit_s: int = 150) -> dict:
+    """cpu_baseline / cpu_baseline_torch in a child process with a time limit: a slow or oversubscribed host can cost
+    the bench line its CPU baseline, never the line itself."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-baseline-child", kind, "--gaussians", str(args.gaussians),
+           "--detector", str(args.detector), "--views", str(args.views), "--cloud", args.cloud]
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", CUDA_VISIBLE_DEVICES="")
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit_s, env=env, cwd=ROOT)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}", "kind": kind}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {limit_s} s on this host ({usable_cores()} usable cores)", "kind": kind}
+
+
 def cpu_baseline(cloud, views, n_proj=2):
     from oracle import r2_oracle as orc
 
     orc.lib()
+    orc.set_num_threads(usable_cores())
     t0 = time.perf_counter()
     for i in range(n_proj):
         v = views[i % len(views)]
@@ -215,7 +249,7 @@ def cpu_baseline_torch(cloud, views, n_proj=3):
     import torch
 
     from oracle import torch_projector as tp
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     v = views[0]
     tp.project(cloud.means, cloud.density, cloud.scales, cloud.rotations, v.viewmatrix, v.projmatrix, v.image_width,
@@ -416,12 +450,19 @@ def run_ours(args, rank, world, local_rank):
                 "timed": "r2x_raster_render_only = two small memsets (queue head, arrival counters) + the render kernel, CUDA events, L2 flushed",
                 "note": "kernel is FP32-issue-bound (multiplicative forward differences: ~5 issue slots and 0.5 "
                         "MUFU.EX2 per pixel-Gaussian pair), not HBM-bound; see DESIGN.md section 5"}
-    try:   # the bound that does apply: one MUFU.EX2 per pair; 15.85 ex2/clk/SM measured (scripts/micro/mufu_rate.cu)
+    try:   # the bounds that do apply (both measured on this part, scripts/micro/): MUFU.EX2 rate and the FP32 issue rate
         props = torch.cuda.get_device_properties(dev)
         mhz = float(sampler.summary().get("sm_mhz") or 0.0) or 1965.0
-        ex2_peak = 15.85 * props.multi_processor_count * mhz * 1e6
-        roofline["mufu"] = {"achieved": pairs / t_render, "peak": ex2_peak, "unit": "ex2/s", "frac": pairs / t_render / ex2_peak,
-                            "peak_source": f"15.85 ex2/clk/SM (measured) x {props.multi_processor_count} SMs x {mhz:.0f} MHz"}
+        sms = props.multi_processor_count
+        ex2_peak = 15.85 * sms * mhz * 1e6
+        roofline["mufu"] = {"achieved": 0.5 * pairs / t_render, "peak": ex2_peak, "unit": "ex2/s",
+                            "frac": 0.5 * pairs / t_render / ex2_peak, "ex2_per_pair": 0.5,
+                            "peak_source": f"15.85 ex2/clk/SM (measured, mufu_rate.cu) x {sms} SMs x {mhz:.0f} MHz"}
+        loop_peak = 19.9 * sms * mhz * 1e6
+        roofline["issue"] = {"achieved": pairs / t_render, "peak": loop_peak, "unit": "pairs/s", "frac": pairs / t_render / loop_peak,
+                             "peak_source": f"19.9 pairs/clk/SM: the kernel's inner loop (f32x2 multiplicative differences) alone, "
+                                            f"all operands in registers (measured, render_loop4.cu; profiles/r02_micro_render_loop4.txt) "
+                                            f"x {sms} SMs x {mhz:.0f} MHz"}
     except Exception as e:   # informational only
         roofline["mufu"] = {"error": str(e)}
 
@@ -546,8 +587,10 @@ def run_ours(args, rank, world, local_rank):
         result["secondary"] = secondary.measure(dev, peak, trace=trace)
         trace("secondary done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(cloud, views, 2)
-        result["cpu_baseline_torch"] = cpu_baseline_torch(cloud, views, 3)
+        result["cpu_baseline"] = guarded_cpu_baseline(args, "port")
+        trace("cpu baseline (oracle port)")
+        result["cpu_baseline_torch"] = guarded_cpu_baseline(args, "torch")
+        trace("cpu baseline (torch projector)")
     return result
 
 
@@ -656,9 +699,7 @@ def run_reference(args):
                              "'ours' arm (the generic contract's 0 bytes assumes a CPU reference)"})
     base["config"]["num_rendered_mean"] = float(np.mean(Rs[-args.steps:]))
     if not args.no_cpu_baseline:
-        cb = cpu_baseline(cloud, views, 2)
-        cb["kind"] = "port"
-        base["cpu_baseline"] = cb
+        base["cpu_baseline"] = guarded_cpu_baseline(args, "port")
     return base
 
 
@@ -668,6 +709,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.cpu_baseline_child:
+        _sc, views, cloud = build_scene(args)
+        fn = cpu_baseline if args.cpu_baseline_child == "port" else cpu_baseline_torch
+        print(json.dumps(fn(cloud, views)), flush=True)
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
