@@ -66,6 +66,38 @@ def main():
     t_wall = time.perf_counter() - t0
     out = {"wall_ms_per_iteration": t_wall / n * 1e3, "host_enqueue_ms_per_iteration": t_enq / n * 1e3,
            "fused_activations": os.environ.get("R2X_FUSED_ACTIVATIONS", "default")}
+    # the same iteration as a fixed launch sequence (what trainer.py runs)
+    from r2_gaussian_b200.train_step import NativeTrainStep
+    native = NativeTrainStep(gm, 0.25, 0.05, [32, 32, 32], [0.25, 0.25, 0.25])
+
+    def native_iter():
+        i = it[0] = it[0] + 1
+        gm.update_learning_rate(i)
+        native(cams[i % 8], gts[i % 8], (0.1, 0.0, -0.1))
+
+    for _ in range(10):
+        native_iter()
+    native.flush()
+    torch.cuda.synchronize()
+    nn = 300
+    t0 = time.perf_counter()
+    for _ in range(nn):
+        native_iter()
+    t_enq = time.perf_counter() - t0
+    native.flush()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t0
+    out["native_wall_ms_per_iteration"] = t_wall / nn * 1e3
+    out["native_host_enqueue_ms_per_iteration"] = t_enq / nn * 1e3
+    out["native_repeats"] = native.repeats
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(nn):
+        native_iter()
+    ev1.record()
+    native.flush()
+    torch.cuda.synchronize()
+    out["native_gpu_ms_per_iteration_events"] = ev0.elapsed_time(ev1) / nn
     if os.environ.get("TRAIN_CPROFILE"):      # where the HOST time of an iteration goes, Python frames included
         import cProfile
         import pstats
