@@ -101,6 +101,12 @@ TilePlan carve_plan(const void* image_buf, int tiles, const BinningView& bv) {
     char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2));
     return plan_view(p, tiles, bv);
 }
+// voxelizer: work items may hold up to VOX_CHUNK_CAP instances (walked in segments), see plan_chunk_for
+TilePlan carve_voxel_plan(const void* image_buf, int tiles, const BinningView& bv) {
+    TilePlan pl = carve_plan(image_buf, tiles, bv);
+    pl.chunk_cap = VOX_CHUNK_CAP;
+    return pl;
+}
 DirectBin carve_directbin(const void* image_buf, int P, int tiles) {
     char* p = (char*)al((size_t)image_buf) + al((size_t)tiles * sizeof(uint2)) + plan_bytes(tiles);
     return directbin_view(p, P, tiles);
@@ -361,7 +367,7 @@ int voxel_forward_impl(cudaStream_t st, int P, int nx, int ny, int nz, float sx,
         R_launch = capacity;
     }
     BinningView bv = binning_view(binning_buf, capacity);
-    const TilePlan plan = carve_plan(image_buf, tiles, bv);
+    const TilePlan plan = carve_voxel_plan(image_buf, tiles, bv);
     if (direct) {
         R2X_TRY(launch_direct_fill(st, P, s.geom.cube, s.geom.tiles_touched, s.geom.offsets, db, ranges, plan, bv, vg.gx,
                                    vg.gy, s.status));
@@ -456,7 +462,7 @@ int r2x_voxel_render_only(void* stream, int P, int nx, int ny, int nz, long long
     VoxelState s = carve_voxel(geom_buf, P);
     BinningView bv = binning_view((void*)binning_buf, R);
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
-    const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
+    const TilePlan plan = carve_voxel_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
     R2X_CUDA_OK(cudaMemsetAsync(plan.counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     R2X_CUDA_OK(cudaMemsetAsync(plan.tile_done, 0, sizeof(uint32_t) * PLAN_DONE_SLOTS * (size_t)plan.num_tiles, (cudaStream_t)stream));
     return launch_voxel_render((cudaStream_t)stream, vg, s.geom, ranges, bv.point_list, plan, R, out_volume);
@@ -567,7 +573,7 @@ int r2x_voxel_backward(void* stream, int P, long long R, int nx, int ny, int nz,
     const uint2* ranges = (const uint2*)al((size_t)image_buf);
     BinningView bv = binning_view((void*)binning_buf, R);
     float4* inst_grad = (float4*)al((size_t)scratch);
-    const TilePlan plan = carve_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
+    const TilePlan plan = carve_voxel_plan(image_buf, vg.gx * vg.gy * vg.gz, bv);
     // direct and two-level binning keep no per-instance slot array: the slots are derived (emission_slot())
     const uint32_t* inst_pos = (direct_ok(vg.gx * vg.gy * vg.gz) || two_level_ok(vg.gx, vg.gy, vg.gz)) ? nullptr : bv.inst_pos;
     if (R > 0) R2X_TRY(launch_voxel_render_bwd(st, vg, s.geom, ranges, bv.point_list, inst_pos, plan, R, dL_dvol, inst_grad));

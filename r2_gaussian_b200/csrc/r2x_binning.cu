@@ -63,6 +63,7 @@ TilePlan plan_view(void* buf, int num_tiles, const BinningView& bv) {
     pl.partial = bv.partial;
     pl.num_tiles = num_tiles;
     pl.chunk_override = plan_chunk_override();
+    pl.chunk_cap = PLAN_CHUNK;
     pl.max_extra = (long long)plan_items(bv.capacity);
     return pl;
 }
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint2* __restrict__ ra
     __syncthreads();
     if (lane == 0) atomicMax(&s_carry, Rloc);
     __syncthreads();
-    const uint32_t C = plan_chunk_for(s_carry, pl.chunk_override);
+    const uint32_t C = plan_chunk_for(s_carry, pl.chunk_override, pl.chunk_cap);
     __syncthreads();
     if (tid == 0) s_carry = 0;
     if (tid < 2) pl.counter[tid] = 0;
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(DIRECT_BLOCK) direct_fill_kernel(int P, const 
     // Overflow (asynchronous variant only): the binning buffer cannot hold the lists, so EMPTY ranges are
     // published -- the render then produces zeros without touching unwritten list entries -- and the host sees
     // status[1] = 1 (direct_scan) and re-runs with a larger buffer.
-    const uint32_t C = plan_chunk_for(status[0], pl.chunk_override);   // status[0] = R (direct_scan)
+    const uint32_t C = plan_chunk_for(status[0], pl.chunk_override, pl.chunk_cap);   // status[0] = R (direct_scan)
     const int npub = db.nb < DIRECT_BLOCK ? db.nb : DIRECT_BLOCK;
     const bool pub = (b < npub) && (tid % npub == b);
     const unsigned long long tot = cta_exclusive_scan_1pass<unsigned long long>(

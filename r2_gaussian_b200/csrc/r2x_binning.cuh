@@ -56,16 +56,23 @@ struct TilePlan {
     float* partial;       // [R/PLAN_MIN_CHUNK + 1][512] partial sums of extra chunks      (binning buffer)
     int num_tiles;
     int chunk_override;   // 0 = automatic (plan_chunk_for); else the chunk size to use (R2X_CHUNK, experiments)
+    int chunk_cap;        // largest chunk the consumer kernels take: PLAN_CHUNK (rasterizer: records staged per item),
+                          // VOX_CHUNK_CAP (voxelizer: an item is walked in segments of PLAN_CHUNK records)
     long long max_extra;  // entries in extra_item / partial
 };
-__host__ __device__ __forceinline__ uint32_t plan_chunk_for(uint32_t R, int chunk_override) {
-    if (chunk_override > 0) return (uint32_t)(chunk_override < PLAN_MIN_CHUNK ? PLAN_MIN_CHUNK : (chunk_override > PLAN_CHUNK ? PLAN_CHUNK : chunk_override));
-    // Measured (B200, warp-specialised render kernel): the largest chunk wins at every instance count -- 256 vs 192 / 128 /
-    // 64 on the 1.06 M-instance headline scene: 78 / 84 / 97 / 132 us -- because a work item costs the producer warp a
-    // fixed latency chain; small shards (one chunk per tile) are bound by that chain, not by the math.  The device-side
-    // choice is kept as a mechanism (R2X_CHUNK for experiments).
-    (void)R;
-    return (uint32_t)PLAN_CHUNK;
+constexpr int VOX_CHUNK_CAP = 4096;
+__host__ __device__ __forceinline__ uint32_t plan_chunk_for(uint32_t R, int chunk_override, int chunk_cap) {
+    const uint32_t cap = (uint32_t)(chunk_cap > PLAN_CHUNK ? chunk_cap : PLAN_CHUNK);
+    if (chunk_override > 0) return (uint32_t)(chunk_override < PLAN_MIN_CHUNK ? PLAN_MIN_CHUNK : ((uint32_t)chunk_override > cap ? cap : (uint32_t)chunk_override));
+    // Rasterizer (cap = PLAN_CHUNK).  Measured (B200, warp-specialised render kernel): the largest chunk wins at every
+    // instance count -- 256 vs 192 / 128 / 64 on the 1.06 M-instance headline scene: 78 / 84 / 97 / 132 us -- because a
+    // work item costs the producer warp a fixed latency chain.
+    if (cap <= (uint32_t)PLAN_CHUNK) return (uint32_t)PLAN_CHUNK;
+    // Voxelizer (cap = VOX_CHUNK_CAP): a tile list is only cut when that is needed to keep a few thousand work items
+    // in the queue (64 tiles of a TV crop over 592 CTAs: chunks of 256; 32768 tiles of a 256^3 query: one item per tile,
+    // so no partial sums leave the CTA and no arrival counters are touched).
+    const uint32_t want = (R / 4096u + (uint32_t)PLAN_CHUNK - 1u) / (uint32_t)PLAN_CHUNK * (uint32_t)PLAN_CHUNK;
+    return want < (uint32_t)PLAN_CHUNK ? (uint32_t)PLAN_CHUNK : (want > cap ? cap : want);
 }
 int plan_chunk_override();   // R2X_CHUNK from the environment (0 when unset)
 size_t plan_bytes(int num_tiles);

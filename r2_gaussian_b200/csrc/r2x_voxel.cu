@@ -264,6 +264,16 @@ __device__ __forceinline__ void voxel_exact_8(float (&acc)[8], const float4 r0, 
     }
 }
 
+// A work item (tile, chunk) holds up to VOX_CHUNK_CAP instances; the CTA walks it in SEGMENTS of <= VR_THREADS records
+// (what one staging buffer holds), keeps the 8 voxel sums of every thread in registers across the segments, and runs
+// the epilogue (cross-slice reduction, store, multi-chunk arrival) once per item.  The stream of segments is
+// double-buffered exactly like the items used to be: segment A computes while B's records land and C's ids are read.
+struct VSeg {
+    int tile, chunk, nch, n;
+    uint32_t begin;
+    bool valid, first, last;
+};
+
 __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, const uint2* __restrict__ ranges,
                                                                   const uint32_t* __restrict__ point_list,
                                                                   const float4* __restrict__ rec, TilePlan pl,
@@ -278,12 +288,39 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
     const int lx = q >> 3, ly = q & 7;
     const uint32_t total = (uint32_t)pl.num_tiles + pl.extra_off[pl.num_tiles];
 
+    // segment stream (all of it uniform across the CTA)
+    VWorkItem it;
+    it.valid = false; it.tile = 0; it.chunk = 0; it.nch = 1; it.n = 0; it.begin = 0;
+    int handed = 0;          // instances of `it` already handed out
+    bool has = false;        // `it` still has a segment to hand out
+    uint32_t resv = 0, resv_end = 0;   // item indices reserved from the queue, not yet decoded
+    auto refill = [&](uint32_t idx) {
+        it = vfetch_item(pl, ranges, idx, total);
+        handed = 0;
+        has = it.valid;
+    };
+    auto take = [&]() {
+        VSeg sg;
+        sg.valid = has;
+        sg.tile = it.tile; sg.chunk = it.chunk; sg.nch = it.nch;
+        sg.begin = it.begin + (uint32_t)handed;
+        const int rem = it.n - handed;
+        sg.n = has ? (rem < VR_THREADS ? rem : VR_THREADS) : 0;
+        sg.first = has && handed == 0;
+        handed += sg.n;
+        sg.last = has && handed >= it.n;
+        if (sg.last) has = false;
+        return sg;
+    };
+
     if (tid == 0) s_next = atomicAdd(&pl.counter[0], 2u);
     __syncthreads();
-    const uint32_t first = s_next;
+    resv = s_next; resv_end = resv + 2;
     __syncthreads();
-    VWorkItem A = vfetch_item(pl, ranges, first, total);
-    VWorkItem B = vfetch_item(pl, ranges, first + 1, total);
+    refill(resv++);
+    VSeg A = take();
+    if (!has) refill(resv++);
+    VSeg B = take();
     uint32_t idB = 0;
     if (A.valid && tid < A.n) {
         const uint32_t id = point_list[A.begin + tid];
@@ -294,9 +331,13 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
     cp_async_commit();
     if (B.valid && tid < B.n) idB = point_list[B.begin + tid];
     int stage = 0;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
 
     while (A.valid) {
-        if (tid == 0) s_next = atomicAdd(&pl.counter[0], 1u);
+        const bool need_atomic = !has && resv >= resv_end;
+        if (need_atomic && tid == 0) s_next = atomicAdd(&pl.counter[0], 1u);
         if (B.valid && tid < B.n) {
             cp_async16(&s_rec[stage ^ 1][tid][0], &rec[4 * (size_t)idB]);
             cp_async16(&s_rec[stage ^ 1][tid][1], &rec[4 * (size_t)idB + 1]);
@@ -305,7 +346,8 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
         cp_async_commit();
         cp_async_wait<1>();
         const int any_exact = __syncthreads_or((tid < A.n) && (s_rec[stage][tid][2].w != 0.0f));
-        VWorkItem Cw = vfetch_item(pl, ranges, s_next, total);
+        if (!has) refill(resv < resv_end ? resv++ : s_next);
+        VSeg Cw = take();
         uint32_t idC = 0;
         if (Cw.valid && tid < Cw.n) idC = point_list[Cw.begin + tid];
 
@@ -313,9 +355,10 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
         const float fx = (float)(tx * R2X_VTILE + lx) + 0.5f;
         const float fy = (float)(ty * R2X_VTILE + ly) + 0.5f;
         const float fz0 = (float)(tz * R2X_VTILE) + 0.5f;
-        float acc[8];
+        if (A.first) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        }
         if (!any_exact) {
 #pragma unroll 2
             for (int j = slice; j < A.n; j += VR_SLICES)
@@ -327,59 +370,63 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_render_kernel(VoxelGrid vg, 
                 else voxel_exact_8(acc, r0, r1, r2, fx, fy, fz0);
             }
         }
-        if (slice > 0) {
+        if (A.last) {
+            if (slice > 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s_red[slice - 1][q][k] = acc[k];
-        }
-        __syncthreads();
-        const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z0 = tz * R2X_VTILE;
-        const bool col_in = (x < vg.nx && y < vg.ny);
-        float* dst = out_volume + ((size_t)x * vg.ny + y) * vg.nz + z0;
-        if (slice == 0) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                v[k] = acc[k];
-                v[k] += s_red[0][q][k];
-                v[k] += s_red[1][q][k];
-                v[k] += s_red[2][q][k];
+                for (int k = 0; k < 8; ++k) s_red[slice - 1][q][k] = acc[k];
             }
-            if (A.chunk == 0) {
-                if (col_in) {
+            __syncthreads();
+            const int x = tx * R2X_VTILE + lx, y = ty * R2X_VTILE + ly, z0 = tz * R2X_VTILE;
+            const bool col_in = (x < vg.nx && y < vg.ny);
+            float* dst = out_volume + ((size_t)x * vg.ny + y) * vg.nz + z0;
+            if (slice == 0) {
+                float v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (z0 + k < vg.nz) dst[k] = v[k];
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = acc[k];
+                    v[k] += s_red[0][q][k];
+                    v[k] += s_red[1][q][k];
+                    v[k] += s_red[2][q][k];
                 }
-            } else {
-                const size_t slot = (size_t)(pl.extra_off[A.tile] + A.chunk - 1);
-                float4* ps = reinterpret_cast<float4*>(&pl.partial[slot * 512 + q * 8]);
-                ps[0] = make_float4(v[0], v[1], v[2], v[3]);
-                ps[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-        }
-        if (A.nch > 1) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) s_last = (atomicAdd(&pl.tile_done[A.tile], 1u) == (uint32_t)(A.nch - 1)) ? 1u : 0u;
-            __syncthreads();
-            if (s_last) {
-                __threadfence();
-                if (slice == 0 && col_in) {
-                    const size_t base = (size_t)pl.extra_off[A.tile];
-                    float v[8];
+                if (A.chunk == 0) {
+                    if (col_in) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = (z0 + k < vg.nz) ? __ldcg(&dst[k]) : 0.f;
-                    for (int c = 1; c < A.nch; ++c) {
-                        const float4* ps = reinterpret_cast<const float4*>(&pl.partial[(base + c - 1) * 512 + q * 8]);
-                        const float4 p0 = __ldcg(ps), p1 = __ldcg(ps + 1);
-                        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-                        v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                        for (int k = 0; k < 8; ++k)
+                            if (z0 + k < vg.nz) dst[k] = v[k];
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (z0 + k < vg.nz) dst[k] = v[k];
+                } else {
+                    const size_t slot = (size_t)(pl.extra_off[A.tile] + A.chunk - 1);
+                    float4* ps = reinterpret_cast<float4*>(&pl.partial[slot * 512 + q * 8]);
+                    ps[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    ps[1] = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
+            if (A.nch > 1) {
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) s_last = (atomicAdd(&pl.tile_done[A.tile], 1u) == (uint32_t)(A.nch - 1)) ? 1u : 0u;
+                __syncthreads();
+                if (s_last) {
+                    __threadfence();
+                    if (slice == 0 && col_in) {
+                        const size_t base = (size_t)pl.extra_off[A.tile];
+                        float v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = (z0 + k < vg.nz) ? __ldcg(&dst[k]) : 0.f;
+                        for (int c = 1; c < A.nch; ++c) {
+                            const float4* ps = reinterpret_cast<const float4*>(&pl.partial[(base + c - 1) * 512 + q * 8]);
+                            const float4 p0 = __ldcg(ps), p1 = __ldcg(ps + 1);
+                            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (z0 + k < vg.nz) dst[k] = v[k];
+                    }
+                }
+            }
+        } else {
+            __syncthreads();   // every thread is done with s_rec[stage] before the next segment's records land in it
         }
         A = B; B = Cw; idB = idC; stage ^= 1;
     }
@@ -419,10 +466,10 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
             cur_tile = tile;
         }
         __syncthreads();
-        if (tid >= n) continue;
+        for (int ii = tid; ii < n; ii += 256) {   // an item holds up to VOX_CHUNK_CAP instances: 256 per sweep
         const float fx0 = (float)(tx * R2X_VTILE) + 0.5f, fy0 = (float)(ty * R2X_VTILE) + 0.5f,
                     fz0 = (float)(tz * R2X_VTILE) + 0.5f;
-        const uint32_t s = begin + tid;
+        const uint32_t s = begin + (uint32_t)ii;
         const uint32_t g = point_list[s];
         const float4 r0 = rec[4 * (size_t)g];
         const float4 r1 = rec[4 * (size_t)g + 1];
@@ -499,6 +546,7 @@ __global__ void __launch_bounds__(256) voxel_render_bwd_kernel(VoxelGrid vg, con
         inst_grad[3 * (size_t)slot] = make_float4(S0, Sx, Sy, Sz);
         inst_grad[3 * (size_t)slot + 1] = make_float4(Sxx, Sxy, Sxz, Syy);
         inst_grad[3 * (size_t)slot + 2] = make_float4(Syz, Szz, 0.f, 0.f);
+        }
     }
 }
 

@@ -50,6 +50,19 @@ def sharded_sum(x: torch.Tensor) -> torch.Tensor:
     return all_reduce_sum(x, _SHARD["group"]) if enabled() else x
 
 
+def sharded_sum_(x: torch.Tensor) -> torch.Tensor:
+    """In-place, autograd-free form of sharded_sum (train_step.NativeTrainStep): x becomes the sum over the ranks."""
+    if not enabled() or dist.get_world_size(_SHARD["group"]) == 1:
+        return x
+    group = _SHARD["group"]
+    if _PEER["on"] and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous():
+        red = _peer_reducer(x, group)
+        red.partial().view_as(x).copy_(x)
+        return red.reduce(x)
+    dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+    return x
+
+
 def check_peer_exchange():
     """Raise if any peer-memory reduction since the last check gave up waiting for a peer (the kernel sets a status word
     instead of hanging the GPU, and then sums whatever the late peer's buffer held).  Synchronises; the trainer calls it

@@ -184,9 +184,7 @@ class NativeTrainStep:
                 proj.data_ptr(), campos.data_ptr(), tfx, tfy, mode, self.image.data_ptr(), self.radii.data_ptr(),
                 self.geom.data_ptr(), self.img.data_ptr(), self.binning_r.data_ptr(), self.cap_r, self.status_r.data_ptr(),
                 act), "r2x_raster_forward_async_raw")
-            image = self.image
-            if sharded.enabled():
-                image = sharded.sharded_sum(image)
+            image = sharded.sharded_sum_(self.image)      # identity unless Gaussian-sharded
             check(lib.r2x_image_loss(st, H, W, image.data_ptr(), gt.data_ptr(), 1.0, self.lambda_dssim,
                                      self.loss_out.data_ptr(), self.dL_dimage.data_ptr(), self.loss_scratch.data_ptr(),
                                      self.loss_scratch_bytes), "r2x_image_loss")
@@ -197,9 +195,7 @@ class NativeTrainStep:
                     st, P, *grid, xyz.data_ptr(), dens.data_ptr(), scal.data_ptr(), sm, rot.data_ptr(), self.vol.data_ptr(),
                     self.rx.data_ptr(), self.ry.data_ptr(), self.rz.data_ptr(), self.geom_v.data_ptr(), self.img_v.data_ptr(),
                     self.binning_v.data_ptr(), self.cap_v, self.status_v.data_ptr(), act), "r2x_voxel_forward_async_raw")
-                vol = self.vol
-                if sharded.enabled():
-                    vol = sharded.sharded_sum(vol)
+                vol = sharded.sharded_sum_(self.vol)
                 check(lib.r2x_tv3d_loss(st, nx, ny, nz, vol.data_ptr(), 1, self.tv_out.data_ptr(), self.dL_dvol.data_ptr(),
                                         self.tv_scratch.data_ptr(), self.tv_scratch_bytes), "r2x_tv3d_loss")
                 self.dL_dvol.mul_(self.lambda_tv)
