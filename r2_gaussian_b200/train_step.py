@@ -56,7 +56,7 @@ class NativeTrainStep:
     # ------------------------------------------------------------------ buffers
     def _signature(self, H, W):
         gm = self.gm
-        return (gm._xyz.data_ptr(), gm._density.data_ptr(), gm._scaling.data_ptr(), gm._rotation.data_ptr(),
+        return (sharded.enabled(), gm._xyz.data_ptr(), gm._density.data_ptr(), gm._scaling.data_ptr(), gm._rotation.data_ptr(),
                 int(gm._xyz.shape[0]), H, W, gm.max_radii2D.data_ptr(), gm.xyz_gradient_accum.data_ptr())
 
     def _bind(self, H, W):
@@ -68,8 +68,13 @@ class NativeTrainStep:
         u8 = dict(dtype=torch.uint8, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            # raster
-            self.image = torch.empty((1, H, W), **f32)
+            # raster.  Gaussian-sharded runs: the image travels through the exchange with one extra word, this rank's
+            # overflow flag, so that after the sum EVERY rank knows whether ANY rank's forward overflowed (the summed
+            # image is then wrong everywhere) and all ranks skip / repeat the iteration together.
+            self.sharded = sharded.enabled()
+            self.image_ext = torch.zeros(H * W + 4, **f32)
+            self.image = self.image_ext[:H * W].view(1, H, W)
+            self.flag_r = self.image_ext[H * W:H * W + 1]
             self.radii = torch.empty((P,), **i32)
             self.geom = torch.empty(lib.r2x_raster_geom_bytes(P), **u8)
             self.img = torch.empty(lib.r2x_raster_image_bytes(P, W, H), **u8)
@@ -85,7 +90,9 @@ class NativeTrainStep:
             # TV crop
             if self.use_tv:
                 nx, ny, nz = self.tv_n
-                self.vol = torch.empty((nx, ny, nz), **f32)
+                self.vol_ext = torch.zeros(nx * ny * nz + 4, **f32)
+                self.vol = self.vol_ext[:nx * ny * nz].view(nx, ny, nz)
+                self.flag_v = self.vol_ext[nx * ny * nz:nx * ny * nz + 1]
                 self.rx = torch.empty((P,), **i32); self.ry = torch.empty((P,), **i32); self.rz = torch.empty((P,), **i32)
                 self.geom_v = torch.empty(lib.r2x_voxel_geom_bytes(P), **u8)
                 self.img_v = torch.empty(lib.r2x_voxel_image_bytes(P, nx, ny, nz), **u8)
@@ -184,7 +191,11 @@ class NativeTrainStep:
                 proj.data_ptr(), campos.data_ptr(), tfx, tfy, mode, self.image.data_ptr(), self.radii.data_ptr(),
                 self.geom.data_ptr(), self.img.data_ptr(), self.binning_r.data_ptr(), self.cap_r, self.status_r.data_ptr(),
                 act), "r2x_raster_forward_async_raw")
-            image = sharded.sharded_sum_(self.image)      # identity unless Gaussian-sharded
+            image = self.image
+            if self.sharded:
+                self.flag_r.copy_(self.status_r[1:2])          # my overflow flag rides with the image
+                sharded.sharded_sum_(self.image_ext)
+                self.status_r[1:2].copy_(self.flag_r)          # ... and comes back as "any rank overflowed"
             check(lib.r2x_image_loss(st, H, W, image.data_ptr(), gt.data_ptr(), 1.0, self.lambda_dssim,
                                      self.loss_out.data_ptr(), self.dL_dimage.data_ptr(), self.loss_scratch.data_ptr(),
                                      self.loss_scratch_bytes), "r2x_image_loss")
@@ -195,7 +206,11 @@ class NativeTrainStep:
                     st, P, *grid, xyz.data_ptr(), dens.data_ptr(), scal.data_ptr(), sm, rot.data_ptr(), self.vol.data_ptr(),
                     self.rx.data_ptr(), self.ry.data_ptr(), self.rz.data_ptr(), self.geom_v.data_ptr(), self.img_v.data_ptr(),
                     self.binning_v.data_ptr(), self.cap_v, self.status_v.data_ptr(), act), "r2x_voxel_forward_async_raw")
-                vol = sharded.sharded_sum_(self.vol)
+                vol = self.vol
+                if self.sharded:
+                    self.flag_v.copy_(self.status_v[1:2])
+                    sharded.sharded_sum_(self.vol_ext)
+                    self.status_v[1:2].copy_(self.flag_v)
                 check(lib.r2x_tv3d_loss(st, nx, ny, nz, vol.data_ptr(), 1, self.tv_out.data_ptr(), self.dL_dvol.data_ptr(),
                                         self.tv_scratch.data_ptr(), self.tv_scratch_bytes), "r2x_tv3d_loss")
                 self.dL_dvol.mul_(self.lambda_tv)
