@@ -181,9 +181,22 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     if train_step.enabled() and not getattr(pipe, "debug", False) and not getattr(pipe, "compute_cov3D_python", False):
         native = train_step.NativeTrainStep(gaussians, opt.lambda_dssim, opt.lambda_tv if use_tv else 0.0, tv_n,
                                             [float(v) for v in tv_s])
+    if world > 1:
+        # one exchange of each shape before the clock starts: the NCCL communicator / the peer-memory reducers are
+        # created on first use (seconds at 8 ranks), which is set-up, not a training step
+        cam0 = scene.getTrainCameras()[0]
+        sharded.sharded_sum_(torch.zeros(int(cam0.image_height) * int(cam0.image_width) + 4, device="cuda"))
+        sharded.sharded_sum_(torch.zeros((int(cam0.image_height), int(cam0.image_width)), device="cuda").unsqueeze(0))
+        if use_tv:
+            nvox = int(tv_n[0]) * int(tv_n[1]) * int(tv_n[2])
+            sharded.sharded_sum_(torch.zeros(nvox + 4, device="cuda"))
+            sharded.sharded_sum_(torch.zeros(tuple(int(v) for v in tv_n), device="cuda"))
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
     torch.cuda.synchronize()
     t_start = time.perf_counter()
     t_aside = 0.0     # seconds spent saving / checkpointing / evaluating (reported apart from the training steps)
+    t_mark = None     # (time, aside so far, iteration) after the first iterations: allocator / capacity hints warmed up
 
     class _aside:     # times a block that is not a training step; synchronises on both sides so it owns its GPU time
         def __enter__(self):
@@ -197,6 +210,9 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
             return False
 
     for iteration in range(first_iter + 1, opt.iterations + 1):
+        if t_mark is None and iteration - first_iter == 51:
+            torch.cuda.synchronize()
+            t_mark = (time.perf_counter(), t_aside, iteration - 1)
         gaussians.update_learning_rate(iteration)
         if not stack:
             stack = scene.getTrainCameras().copy()
@@ -293,6 +309,9 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
     torch.cuda.synchronize()
     history["seconds"] = time.perf_counter() - t_start
     history["train_seconds"] = history["seconds"] - t_aside   # the training steps alone
+    if t_mark is not None and opt.iterations > t_mark[2]:
+        history["steady_ms_per_iteration"] = ((time.perf_counter() - t_mark[0]) - (t_aside - t_mark[1])) / \
+            (opt.iterations - t_mark[2]) * 1e3                # after the first 50 iterations (warm allocator / hints)
     history["iterations"] = opt.iterations - first_iter
     history["gaussians"] = int(gaussians.get_xyz.shape[0])
     history["scene"], history["model"] = scene, gaussians
@@ -432,6 +451,8 @@ def main(argv=None):
     print(json.dumps({"seconds": hist["seconds"], "train_seconds": hist["train_seconds"],
                       "ms_per_iteration": hist["train_seconds"] / n_it * 1e3,       # training steps alone
                       "ms_per_iteration_with_save_and_eval": hist["seconds"] / n_it * 1e3,
+                      "steady_ms_per_iteration": hist.get("steady_ms_per_iteration"),
+                      "repeated_iterations": hist.get("repeated_iterations", 0),
                       "gaussians": hist["gaussians"], **final}))
 
 

@@ -46,6 +46,10 @@ def workload():
         gm.create_from_pcd(cloud.means[:20000], np.maximum(cloud.density[:20000], 1e-3), 1.0)
     gm.training_setup(opt_args)
 
+    from r2_gaussian_b200.train_step import NativeTrainStep
+    native = NativeTrainStep(gm, 0.25, 0.05, [32, 32, 32], [0.25, 0.25, 0.25])
+    cam = scene.camera_from_view(view, device=dev)
+
     def once():
         R, img, radii, geom, binning, imgb = _C.rasterize_gaussians(m, d, s, r, 1.0, E, vm, pm, view.tanfovx, view.tanfovy,
                                                                      512, 512, cp, False, view.mode, False)
@@ -56,11 +60,13 @@ def workload():
                                                                  0.1, False, False)
         _C.voxelize_gaussians_backward(m, rx, ry, rz, s, r, 1.0, E, dV, g2, R2, b2, i2, 32, 32, 32, 0.25, 0.25, 0.25, 0.3,
                                        -0.4, 0.1, False)
-        # radix-path backward (volume with more than 4096 tiles)
+        # more than 4096 tiles through the radix path (what grids beyond 512^3 take; the 256^3 call above is two-level)
+        os.environ["R2X_VOXEL_BINNING"] = "radix"
         R3, vol3, ax, ay, az, g3, b3, i3 = _C.voxelize_gaussians(m, d, s, r, 1.0, E, 144, 144, 144, 2.0, 2.0, 2.0, 0.0, 0.0,
                                                                   0.0, False, False)
         _C.voxelize_gaussians_backward(m, ax, ay, az, s, r, 1.0, E, torch.randn_like(vol3), g3, R3, b3, i3, 144, 144, 144,
                                        2.0, 2.0, 2.0, 0.0, 0.0, 0.0, False)
+        del os.environ["R2X_VOXEL_BINNING"]
         a = img.detach().clone().requires_grad_(True)
         losses.image_loss(a, gt, 0.25)["total"].backward()
         v = vol.detach().clone().requires_grad_(True)
@@ -69,6 +75,8 @@ def workload():
             p = getattr(gm, attr)
             p.grad = torch.randn_like(p) * 1e-3
         gm.optimizer.step()
+        native(cam, gt, (0.1, 0.0, -0.1))     # the iteration as a launch sequence (guarded Adam, densification statistics)
+        native.flush()
         distCUDA2(m)
         mask = torch.rand(100_000, device=dev) < 0.5
         idx, cnt = compact.select_rows(mask)
