@@ -161,8 +161,11 @@ class NativeTrainStep:
         H, W = int(cam.image_height), int(cam.image_width)
         if self._bound != self._signature(H, W):
             self._bind(H, W)
-        if self.P == 0:
+        if self.P == 0 and not self.sharded:
             raise RuntimeError("NativeTrainStep: empty model")
+        # an EMPTY SHARD of a Gaussian-sharded run goes through the same sequence: the library calls are no-ops that
+        # produce a zero image / volume (and zero status words), and the rank takes part in both exchanges with the same
+        # buffer sizes as its peers
         args = (cam, gt, None if tv_centre is None else tuple(float(v) for v in tv_centre), bool(apply_update))
         self._enqueue(*args)
         return self.result

@@ -223,7 +223,7 @@ def training(model: ModelParams, opt: OptimizationParams, pipe: PipelineParams, 
         centre = None
         if use_tv:
             centre = (bbox_cpu[0] + tv_s / 2) + (bbox_cpu[1] - tv_s - bbox_cpu[0]) * torch.rand(3)
-        if native is not None and gaussians.get_xyz.shape[0] > 0:
+        if native is not None and (gaussians.get_xyz.shape[0] > 0 or world > 1):
             # fixed launch sequence, no autograd (train_step.py).  At a densification iteration the reference's
             # optimizer.step() comes AFTER the tensors were replaced and therefore applies nothing (their .grad is None,
             # train.py:158-176): the same here.
