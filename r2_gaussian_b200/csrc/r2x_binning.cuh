@@ -96,7 +96,7 @@ __device__ __forceinline__ uint32_t emission_slot(const uint16_t* __restrict__ c
 }
 
 // chunk `chunk` of `nch` equal slices of the tile list [r.x, r.y)
-__device__ __forceinline__ void plan_slice(const uint2 r, int chunk, int nch, uint32_t& begin, int& n) {
+__host__ __device__ __forceinline__ void plan_slice(const uint2 r, int chunk, int nch, uint32_t& begin, int& n) {
     // len = q nch + rem: the first `rem` slices hold q + 1 instances, the others q (one 32-bit division)
     const uint32_t len = r.y - r.x;
     const uint32_t q = len / (uint32_t)nch, rem = len - q * (uint32_t)nch;
