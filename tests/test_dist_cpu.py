@@ -118,6 +118,49 @@ def test_sharding_is_an_explicit_opt_in():
         assert b == [3.0] * 4                                      # 1 + 2 once sharding is enabled
 
 
+def _worker_inplace(rank, world, port, q):
+    """sharded_sum_ (what the native training step exchanges): in place, identity without the opt-in, and the overflow
+    flag that rides behind the image comes back as "any rank overflowed" on every rank."""
+    import torch.distributed as dist
+    from r2_gaussian_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H = W = 4
+        ext = torch.zeros(H * W + 4)
+        image, flag = ext[:H * W].view(1, H, W), ext[H * W:H * W + 1]
+        status = torch.tensor([100 + rank, 1 if rank == 1 else 0], dtype=torch.int32)   # only rank 1 overflowed
+        image.fill_(float(rank + 1))
+        before = sharded.sharded_sum_(ext).clone()                  # no opt-in: untouched
+        sharded.enable()
+        flag.copy_(status[1:2])
+        out = sharded.sharded_sum_(ext)
+        status[1:2].copy_(flag)
+        same_storage = out.data_ptr() == ext.data_ptr()
+        sharded.enable(on=False)
+        q.put((rank, before[:H * W].tolist(), image.flatten().tolist(), status.tolist(), same_storage))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_inplace_exchange_carries_the_overflow_flag():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_inplace, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, before, image, status, same_storage in res:
+        assert before == [rank + 1.0] * 16
+        assert image == [3.0] * 16 and same_storage
+        assert status == [100 + rank, 1]            # the count stays local, the flag is global
+
+
 def test_rank_checkpoint_paths():
     from r2_gaussian_b200.trainer import rank_checkpoint_path
     assert rank_checkpoint_path("ckpt/chkpnt100.pth", 0, 1) == "ckpt/chkpnt100.pth"
